@@ -1,0 +1,634 @@
+// oracle/vmis_oracle.cpp — TEST INFRASTRUCTURE, NOT PRODUCT CODE.
+//
+// CPU restatement of the VMIS-kNN `predict_next` path of bolcom/serenade
+// (reference commit a142ab81), used only as the checker for the CUDA path in
+// serenade_b200/ and as the timed CPU baseline of bench.py.  Only tests/,
+// __graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference legs
+// may load this library.  Nothing under serenade_b200/ links or calls it.
+//
+// Two modes are provided for every query function:
+//   mode 0 "faithful"  — statement-by-statement restatement of the Rust code:
+//       find_neighbors  src/vmisknn/vmis_index.rs:325-415
+//       predict         src/vmisknn/mod.rs:118-215 (+ linear_score :110-116,
+//                       passes_business_rules :162-182)
+//       heaps           std::collections::BinaryHeap sift rules and
+//                       dary_heap::OctonaryHeap (d = 8), restated from their
+//                       published algorithms (neither crate is vendored in
+//                       /root/reference; Cargo.toml:20-46 pins only semver
+//                       ranges: hashbrown "0.11", dary_heap "0.2.2").
+//   mode 1 "canonical" — the closed form of SURVEY.md §7a with total orders
+//       sessions (ts desc, session_idx desc); neighbours (similarity desc,
+//       ts desc, session_idx desc); items (score desc, item_id asc) and exact
+//       integer numerators.  This is what the GPU kernel must match bit-exactly.
+//
+// Index construction restates
+//       prepare_hashmap src/vmisknn/vmis_index.rs:422-528
+//       read_from_file  src/vmisknn/vmis_index.rs:591-752 (incl. the last-row
+//                       quirk at :666-667,675-686)
+//
+// PARITY PINNING STATUS: the Rust reference cannot be built here (no cargo /
+// rustc, crates not vendored, no Cargo.lock).  The oracle is pinned against
+//   (1) the reference's only known-answer test for this path,
+//       should_train_and_predict (mod.rs:229-310),
+//   (2) the heap ordering tests (mod.rs:313-411),
+//   (3) the 21-id response of the shipped binary on the toy data
+//       (README.md:131-155) — same set, same order modulo exact-score ties,
+//   (4) the README evaluator run (README.md:166-177): 931 evaluations,
+//       HitRate@20 0.6402.
+// Tie order at the m / k / n boundaries depends on hashbrown iteration order and
+// heap sift order of un-vendored crates and is NOT pinned by any reference test:
+// "parity unpinned" for exact-tie ordering and for the t-digest p99.5 cut-off.
+//
+// Build: see oracle/Makefile (g++ -O3 -march=x86-64-v3 -shared -fPIC).
+
+#include <algorithm>
+#include <atomic>
+#include <chrono>
+#include <cfloat>
+#include <cmath>
+#include <cstdint>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <numeric>
+#include <string>
+#include <thread>
+#include <vector>
+
+namespace {
+
+// ---------------------------------------------------------------------------
+// Flat open-addressing hash map (stand-in for hashbrown::HashMap).  Iteration is
+// in slot order; the reference's iteration order (hashbrown 0.11 + ahash) is
+// unpinned, so any deterministic order is as faithful as any other.
+// ---------------------------------------------------------------------------
+static inline uint64_t mix64(uint64_t x) {
+  x ^= x >> 33; x *= 0xff51afd7ed558ccdULL; x ^= x >> 33;
+  x *= 0xc4ceb9fe1a85ec53ULL; x ^= x >> 33; return x;
+}
+
+template <class K, class V>
+struct FlatMap {
+  std::vector<K> keys; std::vector<V> vals; std::vector<uint8_t> used;
+  size_t n = 0, mask = 0;
+  explicit FlatMap(size_t cap_hint = 8) { init(cap_hint); }
+  void init(size_t cap_hint) {
+    size_t c = 8; while (c < cap_hint * 2) c <<= 1;
+    keys.assign(c, K()); vals.assign(c, V()); used.assign(c, 0); n = 0; mask = c - 1;
+  }
+  void clear() { std::fill(used.begin(), used.end(), 0); n = 0; }
+  size_t size() const { return n; }
+  size_t slot_of(const K& k) const { return (size_t)mix64((uint64_t)k) & mask; }
+  V* find(const K& k) {
+    size_t s = slot_of(k);
+    while (used[s]) { if (keys[s] == k) return &vals[s]; s = (s + 1) & mask; }
+    return nullptr;
+  }
+  const V* find(const K& k) const { return const_cast<FlatMap*>(this)->find(k); }
+  void grow() {
+    std::vector<K> ok; std::vector<V> ov; std::vector<uint8_t> ou;
+    ok.swap(keys); ov.swap(vals); ou.swap(used);
+    size_t c = (mask + 1) * 2; keys.assign(c, K()); vals.assign(c, V()); used.assign(c, 0);
+    mask = c - 1; n = 0;
+    for (size_t i = 0; i < ou.size(); ++i) if (ou[i]) insert(ok[i], std::move(ov[i]));
+  }
+  // returns pointer to value; *existed tells whether the key was present
+  V* insert(const K& k, V v, bool* existed = nullptr) {
+    if ((n + 1) * 2 > mask + 1) grow();
+    size_t s = slot_of(k);
+    while (used[s]) {
+      if (keys[s] == k) { if (existed) *existed = true; return &vals[s]; }
+      s = (s + 1) & mask;
+    }
+    used[s] = 1; keys[s] = k; vals[s] = std::move(v); ++n;
+    if (existed) *existed = false;
+    return &vals[s];
+  }
+  void erase(const K& k) {  // backward-shift deletion
+    size_t s = slot_of(k);
+    while (used[s]) { if (keys[s] == k) break; s = (s + 1) & mask; }
+    if (!used[s]) return;
+    size_t hole = s, j = s;
+    for (;;) {
+      j = (j + 1) & mask;
+      if (!used[j]) break;
+      size_t home = slot_of(keys[j]);
+      bool movable = (hole <= j) ? (home <= hole || home > j) : (home <= hole && home > j);
+      if (movable) { keys[hole] = keys[j]; vals[hole] = std::move(vals[j]); hole = j; }
+    }
+    used[hole] = 0; --n;
+  }
+};
+
+// ---------------------------------------------------------------------------
+// Ordering types (mod.rs:15-107).  cmp_* return true when a < b in the Rust Ord
+// (which is REVERSED on score / time, so the max-heaps act as min-heaps).
+// ---------------------------------------------------------------------------
+struct SessionScore { uint32_t id; double score; };
+struct ItemScore { uint64_t id; double score; };
+struct SessionTime { uint32_t session_id; uint32_t time; };
+
+// Ord::cmp(a,b) as -1/0/+1 following mod.rs:29-37 / :59-68 (NaN → Equal)
+static inline int ord_score(double a, double b) { return a < b ? +1 : (a > b ? -1 : 0); }
+static inline int ord_time(uint32_t a, uint32_t b) { return b < a ? -1 : (b > a ? +1 : 0); }  // mod.rs:89-93
+
+// d-ary max-heap on an Ord given as int cmp(a,b).  D = 2 restates
+// std::collections::BinaryHeap (sift_up / sift_down_range / into_sorted_vec),
+// D = 8 stands in for dary_heap::OctonaryHeap, which is the same code
+// generalised to d children.
+template <class T, int D, class Cmp>
+struct DHeap {
+  std::vector<T> d; Cmp cmp;
+  size_t size() const { return d.size(); }
+  bool empty() const { return d.empty(); }
+  const T& top() const { return d[0]; }
+  void push(const T& x) { d.push_back(x); sift_up(0, d.size() - 1); }
+  void sift_up(size_t start, size_t pos) {
+    T elt = d[pos];
+    while (pos > start) {
+      size_t parent = (pos - 1) / D;
+      if (cmp(elt, d[parent]) <= 0) break;
+      d[pos] = d[parent]; pos = parent;
+    }
+    d[pos] = elt;
+  }
+  void sift_down_range(size_t pos, size_t end) {
+    T elt = d[pos];
+    for (;;) {
+      size_t first = D * pos + 1;
+      if (first >= end) break;
+      size_t last = std::min(first + D, end);
+      size_t best = first;
+      for (size_t c = first + 1; c < last; ++c) if (cmp(d[best], d[c]) <= 0) best = c;
+      if (cmp(elt, d[best]) >= 0) break;
+      d[pos] = d[best]; pos = best;
+    }
+    d[pos] = elt;
+  }
+  // `*heap.peek_mut().unwrap() = x` followed by PeekMut::drop → sift_down(0)
+  void replace_top(const T& x) { d[0] = x; sift_down_range(0, d.size()); }
+  T pop() {
+    T item = d.back(); d.pop_back();
+    if (!d.empty()) { std::swap(item, d[0]); sift_down_range(0, d.size()); }
+    return item;
+  }
+  // BinaryHeap::into_sorted_vec — ascending in Ord
+  std::vector<T> into_sorted_vec() {
+    size_t end = d.size();
+    while (end > 1) { --end; std::swap(d[0], d[end]); sift_down_range(0, end); }
+    return std::move(d);
+  }
+};
+struct CmpSessionScore { int operator()(const SessionScore& a, const SessionScore& b) const { return ord_score(a.score, b.score); } };
+struct CmpItemScore { int operator()(const ItemScore& a, const ItemScore& b) const { return ord_score(a.score, b.score); } };
+struct CmpSessionTime { int operator()(const SessionTime& a, const SessionTime& b) const { return ord_time(a.time, b.time); } };
+
+// ---------------------------------------------------------------------------
+// Index (vmis_index.rs:28-35)
+// ---------------------------------------------------------------------------
+struct Attr { bool is_adult; bool is_for_sale; };
+struct Index {
+  FlatMap<uint64_t, uint32_t> item_slot;                 // item id -> dense slot in the vectors below
+  std::vector<uint64_t> item_ids;
+  std::vector<std::vector<uint32_t>> item_to_top_sessions_ordered;
+  std::vector<double> item_to_idf_score;
+  std::vector<Attr> item_to_product_attributes;
+  std::vector<uint8_t> item_has_attr;
+  std::vector<uint32_t> session_to_max_time_stamp;
+  std::vector<std::vector<uint64_t>> session_to_items_sorted;   // UN-pruned (vmis_index.rs:79)
+  size_t max_training_session_length = 0;
+  size_t kept_pairs = 0;
+  const std::vector<uint32_t>* postings(uint64_t item) const {
+    const uint32_t* s = item_slot.find(item); return s ? &item_to_top_sessions_ordered[*s] : nullptr;
+  }
+};
+
+// prepare_hashmap (vmis_index.rs:422-528)
+static void prepare_hashmap(Index& ix, size_t m, size_t max_len, double idf_weighting) {
+  const auto& hs = ix.session_to_items_sorted; const auto& ts = ix.session_to_max_time_stamp;
+  std::vector<uint64_t> values; std::vector<uint32_t> sess; std::vector<uint32_t> times;
+  size_t cap = 0; for (auto& s : hs) cap += s.size();
+  values.reserve(cap); sess.reserve(cap); times.reserve(cap);
+  for (size_t sid = 0; sid < hs.size(); ++sid) {
+    if (hs[sid].size() <= max_len) {                                    // :452
+      for (uint64_t it : hs[sid]) { values.push_back(it); sess.push_back((uint32_t)sid); times.push_back(ts[sid]); }
+    }
+  }
+  const size_t P = values.size();
+  ix.kept_pairs = P; ix.max_training_session_length = max_len;
+  std::vector<uint32_t> order(P); std::iota(order.begin(), order.end(), 0u);
+  std::stable_sort(order.begin(), order.end(), [&](uint32_t a, uint32_t b) { return values[a] < values[b]; });  // :466
+  size_t n_items = 0;
+  for (size_t i = 0; i < P; ++i) if (i == 0 || values[order[i]] != values[order[i - 1]]) ++n_items;
+  ix.item_slot.init(n_items + 8);
+  ix.item_ids.reserve(n_items); ix.item_to_top_sessions_ordered.reserve(n_items);
+  ix.item_to_idf_score.reserve(n_items);
+  std::vector<uint32_t> idx;
+  for (size_t left = 0; left < P;) {
+    size_t right = left; const uint64_t item = values[order[left]];
+    while (right + 1 < P && values[order[right + 1]] == item) ++right;     // binary_search_left/right :488-491
+    const size_t cnt = right - left + 1;
+    idx.resize(cnt); std::iota(idx.begin(), idx.end(), 0u);
+    std::stable_sort(idx.begin(), idx.end(), [&](uint32_t a, uint32_t b) {  // :497-498
+      return times[order[left + a]] < times[order[left + b]]; });
+    std::vector<uint32_t> sorted(cnt);
+    for (size_t i = 0; i < cnt; ++i) sorted[i] = sess[order[left + idx[i]]];
+    std::reverse(sorted.begin(), sorted.end());                           // :503
+    if (sorted.size() > m) sorted.resize(m);                              // :504
+    const double idf = std::log((double)P / (double)cnt) * idf_weighting;  // :509-512
+    uint32_t slot = (uint32_t)ix.item_ids.size();
+    ix.item_slot.insert(item, slot);
+    ix.item_ids.push_back(item);
+    ix.item_to_top_sessions_ordered.push_back(std::move(sorted));
+    ix.item_to_idf_score.push_back(idf);
+    ix.item_to_product_attributes.push_back(Attr{false, true});            // :514-517
+    ix.item_has_attr.push_back(1);
+    left = right + 1;
+  }
+}
+
+// exact percentile fallback used when the caller does not pass max_len: the
+// reference uses tdigest 0.2 (unvendored, unpinned) at vmis_index.rs:693-716.
+static size_t exact_p99_5(const std::vector<std::vector<uint64_t>>& hs) {
+  if (hs.empty()) return 0;
+  std::vector<double> lens; lens.reserve(hs.size());
+  for (auto& s : hs) lens.push_back((double)s.size());
+  std::sort(lens.begin(), lens.end());
+  double rank = 0.995 * (double)(lens.size() - 1);
+  size_t lo = (size_t)std::floor(rank), hi = std::min(lo + 1, lens.size() - 1);
+  double v = lens[lo] + (rank - (double)lo) * (lens[hi] - lens[lo]);
+  return (size_t)std::llround(v);
+}
+
+// read_from_file (vmis_index.rs:591-752)
+static bool read_from_file(const char* path, Index& ix) {
+  FILE* f = fopen(path, "rb"); if (!f) return false;
+  std::vector<uint64_t> session_id, item_id, time;
+  char line[4096]; bool header = true;
+  while (fgets(line, sizeof line, f)) {
+    if (header) { header = false; continue; }                             // has_headers(true) :597
+    char* p = line; char* e;
+    unsigned long long a = strtoull(p, &e, 10); if (e == p || *e != '\t') { if (*p && *p != '\n') fprintf(stderr, "Unable to parse input!\n"); continue; }
+    p = e + 1; unsigned long long b = strtoull(p, &e, 10); if (e == p || *e != '\t') { fprintf(stderr, "Unable to parse input!\n"); continue; }
+    p = e + 1; double t = strtod(p, &e); if (e == p) { fprintf(stderr, "Unable to parse input!\n"); continue; }
+    session_id.push_back(a); item_id.push_back(b); time.push_back((uint64_t)std::llround(t));   // :607-613
+  }
+  fclose(f);
+  const size_t n = session_id.size(); if (n == 0) return false;
+  std::vector<uint32_t> ord(n); std::iota(ord.begin(), ord.end(), 0u);
+  std::stable_sort(ord.begin(), ord.end(), [&](uint32_t x, uint32_t y) { return session_id[x] < session_id[y]; });  // :621
+  std::vector<uint64_t> sid(n), iid(n), tim(n);
+  for (size_t i = 0; i < n; ++i) { sid[i] = session_id[ord[i]]; iid[i] = item_id[ord[i]]; tim[i] = time[ord[i]]; }
+  auto& hs = ix.session_to_items_sorted; auto& hts = ix.session_to_max_time_stamp;
+  std::vector<uint64_t> cur; uint64_t max_ts = tim[0];
+  cur.push_back(iid[0]);                                                 // :663
+  for (size_t i = 1; i < n; ++i) {                                        // :666
+    if (sid[i] == sid[i - 1] && i != n - 1) {                             // :667
+      if (std::find(cur.begin(), cur.end(), iid[i]) == cur.end()) {       // :668
+        cur.push_back(iid[i]);
+        if (tim[i] > max_ts) max_ts = tim[i];                             // :671-673
+      }
+    } else {                                                              // :675
+      std::vector<uint64_t> s = cur; std::sort(s.begin(), s.end());       // :676-677
+      hs.push_back(std::move(s)); hts.push_back((uint32_t)max_ts);        // :678-680
+      cur.clear(); cur.push_back(iid[i]); max_ts = tim[i];                // :681-685
+    }
+  }
+  return true;
+}
+
+// ---------------------------------------------------------------------------
+// Faithful query path
+// ---------------------------------------------------------------------------
+static inline double linear_score(size_t pos) { return pos < 100 ? 1.0 - (0.1 * (double)pos) : 0.0; }  // mod.rs:110-116
+
+struct Scratch {
+  FlatMap<uint32_t, double> sims{4096};
+  FlatMap<uint64_t, size_t> hash_items{64};
+  FlatMap<uint64_t, double> item_scores{2048};
+};
+
+// vmis_index.rs:325-415
+static void find_neighbors_faithful(const Index& ix, const uint64_t* ev, size_t L, size_t k, size_t m,
+                                    Scratch& sc, std::vector<SessionScore>& out) {
+  out.clear();
+  DHeap<SessionTime, 8, CmpSessionTime> heap_timestamps;
+  auto& sims = sc.sims; sims.clear();
+  std::vector<uint64_t> uniq(ev, ev + L); std::sort(uniq.begin(), uniq.end());
+  uniq.erase(std::unique(uniq.begin(), uniq.end()), uniq.end());          // :335-337
+  const double qty_unique = (double)uniq.size();
+  auto& hash_items = sc.hash_items; hash_items.clear();
+  for (size_t pos = 0; pos < L; ++pos) {                                  // :344
+    const uint64_t item = ev[L - 1 - pos];
+    bool existed = false; hash_items.insert(item, pos, &existed);          // :346
+    if (existed) continue;
+    const std::vector<uint32_t>* similar = ix.postings(item);             // :350
+    if (!similar) continue;
+    const double decay = (double)(L - pos) / qty_unique;                  // :351-352
+    for (uint32_t sid : *similar) {                                       // :354
+      if (double* s = sims.find(sid)) { *s += decay; continue; }          // :355-356
+      const uint32_t ts = ix.session_to_max_time_stamp[sid];              // :358-359
+      if (sims.size() < m) {                                              // :360
+        sims.insert(sid, decay); heap_timestamps.push(SessionTime{sid, ts});
+      } else {
+        if (heap_timestamps.empty()) break;                               // m == 0 would panic in Rust
+        const SessionTime bottom = heap_timestamps.top();                 // :368
+        if (ts > bottom.time) {                                           // :369
+          sims.erase(bottom.session_id); sims.insert(sid, decay);         // :372-376
+          heap_timestamps.replace_top(SessionTime{sid, ts});              // :377-380
+        } else break;                                                     // :382
+      }
+    }
+  }
+  DHeap<SessionScore, 2, CmpSessionScore> closest;                         // :394
+  for (size_t s = 0; s <= sims.mask; ++s) {                               // :395 (iteration order unpinned)
+    if (!sims.used[s]) continue;
+    const uint32_t sid = sims.keys[s]; const double score = sims.vals[s];
+    if (closest.size() < k) closest.push(SessionScore{sid, score});       // :396-398
+    else {
+      if (closest.empty()) break;
+      const SessionScore bottom = closest.top();                          // :400
+      if (score > bottom.score) closest.replace_top(SessionScore{sid, score});           // :401-403
+      else if (std::fabs(score - bottom.score) < DBL_EPSILON &&
+               ix.session_to_max_time_stamp[sid] > ix.session_to_max_time_stamp[bottom.id])
+        closest.replace_top(SessionScore{sid, score});                    // :404-410
+    }
+  }
+  out = std::move(closest.d);                                             // BinaryHeap::into_iter = backing Vec order
+}
+
+static bool passes_business_rules(const Attr* cur, const Attr* reco) {     // mod.rs:162-182
+  if (!reco) return false;
+  if (reco->is_for_sale) {
+    if (reco->is_adult) { if (cur) return cur->is_adult; return false; }
+    return true;
+  }
+  return false;
+}
+static const Attr* find_attributes(const Index& ix, uint64_t item) {        // vmis_index.rs:417-419
+  const uint32_t* s = ix.item_slot.find(item);
+  if (!s || !ix.item_has_attr[*s]) return nullptr;
+  return &ix.item_to_product_attributes[*s];
+}
+
+// mod.rs:118-215 ; returns the into_sorted_vec() order (score descending)
+static void predict_faithful(const Index& ix, const uint64_t* ev, size_t L, size_t k, size_t m, size_t how_many,
+                             bool biz, Scratch& sc, std::vector<SessionScore>& nb, std::vector<ItemScore>& out) {
+  out.clear();
+  if (L == 0) return;                                                     // Rust panics at :157; callers never pass it
+  find_neighbors_faithful(ix, ev, L, k, m, sc, nb);                       // :126
+  auto& item_scores = sc.item_scores; item_scores.clear();
+  for (const SessionScore& ss : nb) {                                     // :130
+    const std::vector<uint64_t>& titems = ix.session_to_items_sorted[ss.id];   // :131
+    size_t first_match_index = 0; bool found = false;
+    for (size_t i = 0; i < L; ++i) {                                      // :133-138
+      const uint64_t it = ev[L - 1 - i];
+      if (std::find(titems.begin(), titems.end(), it) != titems.end()) { first_match_index = i; found = true; break; }
+    }
+    if (!found) continue;                                                 // unwrap() would panic; cannot happen
+    const double session_weight = linear_score(first_match_index + 1);     // :140-142
+    for (uint64_t it : titems) {                                          // :144
+      const uint32_t* slot = ix.item_slot.find(it);
+      const double item_idf = slot ? ix.item_to_idf_score[*slot] : 0.0;    // :145 (panics if unknown; cannot happen)
+      double* acc = item_scores.insert(it, 0.0);
+      if (item_idf > 0.0) *acc += session_weight * item_idf * ss.score;    // :146-148
+      else *acc += session_weight * ss.score;                              // :150-151
+    }
+  }
+  const uint64_t most_recent = ev[L - 1];                                 // :157
+  item_scores.erase(most_recent);                                         // :158-160
+  DHeap<ItemScore, 2, CmpItemScore> top;                                   // :185
+  const Attr* cur_attr = find_attributes(ix, most_recent);                // :186
+  for (size_t s = 0; s <= item_scores.mask; ++s) {                         // :187 (iteration order unpinned)
+    if (!item_scores.used[s]) continue;
+    const ItemScore cand{item_scores.keys[s], item_scores.vals[s]};
+    if (top.size() < how_many) {                                          // :190
+      if (biz) { if (passes_business_rules(cur_attr, find_attributes(ix, cand.id))) top.push(cand); }
+      else top.push(cand);
+    } else {
+      if (top.empty()) break;
+      if (cand.score > top.top().score) {                                 // :200-201
+        if (biz) { if (passes_business_rules(cur_attr, find_attributes(ix, cand.id))) top.replace_top(cand); }
+        else top.replace_top(cand);
+      }
+    }
+  }
+  out = top.into_sorted_vec();                                            // recommend_resource.rs:58-62
+}
+
+// ---------------------------------------------------------------------------
+// Canonical query path — closed form, exact integers
+// ---------------------------------------------------------------------------
+struct Cand { uint32_t sid; uint32_t ts; int64_t num; };
+
+static void find_neighbors_canonical(const Index& ix, const uint64_t* ev, size_t L, size_t k, size_t m,
+                                     std::vector<Cand>& out, size_t* uniq_out) {
+  out.clear();
+  std::vector<uint64_t> seen; std::vector<std::pair<uint64_t, int64_t>> dist;   // (item, c_j)
+  for (size_t pos = 0; pos < L; ++pos) {
+    const uint64_t item = ev[L - 1 - pos];
+    if (std::find(seen.begin(), seen.end(), item) != seen.end()) continue;
+    seen.push_back(item); dist.push_back({item, (int64_t)(L - pos)});
+  }
+  *uniq_out = dist.size();
+  std::vector<Cand> c;
+  for (auto& d : dist) {
+    const std::vector<uint32_t>* p = ix.postings(d.first); if (!p) continue;
+    for (uint32_t sid : *p) c.push_back(Cand{sid, ix.session_to_max_time_stamp[sid], d.second});
+  }
+  // (ts desc, sid desc); merge duplicates summing numerators
+  std::sort(c.begin(), c.end(), [](const Cand& a, const Cand& b) { return a.ts != b.ts ? a.ts > b.ts : a.sid > b.sid; });
+  std::vector<Cand> u;
+  for (auto& x : c) { if (!u.empty() && u.back().sid == x.sid) u.back().num += x.num; else u.push_back(x); }
+  if (u.size() > m) u.resize(m);
+  std::stable_sort(u.begin(), u.end(), [](const Cand& a, const Cand& b) { return a.num > b.num; });
+  if (u.size() > k) u.resize(k);
+  out.swap(u);
+}
+
+static void predict_canonical(const Index& ix, const uint64_t* ev, size_t L, size_t k, size_t m, size_t how_many,
+                              bool biz, std::vector<ItemScore>& out) {
+  out.clear(); if (L == 0) return;
+  std::vector<Cand> nb; size_t u = 0;
+  find_neighbors_canonical(ix, ev, L, k, m, nb, &u);
+  std::vector<std::pair<uint64_t, int64_t>> contrib;
+  for (const Cand& n : nb) {
+    const std::vector<uint64_t>& titems = ix.session_to_items_sorted[n.sid];
+    size_t p = 0; bool found = false;
+    for (size_t i = 0; i < L && !found; ++i)
+      if (std::find(titems.begin(), titems.end(), ev[L - 1 - i]) != titems.end()) { p = i + 1; found = true; }
+    if (!found) continue;
+    const int64_t w10 = p < 100 ? 10 - (int64_t)p : 0;
+    for (uint64_t it : titems) contrib.push_back({it, w10 * n.num});
+  }
+  std::sort(contrib.begin(), contrib.end(), [](auto& a, auto& b) { return a.first < b.first; });
+  const uint64_t most_recent = ev[L - 1];
+  const Attr* cur_attr = find_attributes(ix, most_recent);
+  std::vector<ItemScore> all;
+  for (size_t i = 0; i < contrib.size();) {
+    size_t j = i; int64_t A = 0;
+    while (j < contrib.size() && contrib[j].first == contrib[i].first) { A += contrib[j].second; ++j; }
+    const uint64_t item = contrib[i].first; i = j;
+    if (item == most_recent) continue;
+    if (biz && !passes_business_rules(cur_attr, find_attributes(ix, item))) continue;
+    const uint32_t* slot = ix.item_slot.find(item);
+    const double idf = slot ? ix.item_to_idf_score[*slot] : 0.0;
+    const double g = idf > 0.0 ? idf : 1.0;
+    all.push_back(ItemScore{item, g * (double)A / (double)(10 * (int64_t)u)});
+  }
+  std::sort(all.begin(), all.end(), [](const ItemScore& a, const ItemScore& b) {
+    return a.score != b.score ? a.score > b.score : a.id < b.id; });
+  if (all.size() > how_many) all.resize(how_many);
+  out.swap(all);
+}
+
+}  // namespace
+
+// ---------------------------------------------------------------------------
+// C ABI for ctypes (tests / bench only)
+// ---------------------------------------------------------------------------
+extern "C" {
+
+void* vo_index_from_sessions(const uint64_t* items, const uint64_t* off, const uint32_t* ts, size_t S,
+                             size_t m, size_t max_len, double idf_w) {
+  Index* ix = new Index();
+  ix->session_to_items_sorted.resize(S); ix->session_to_max_time_stamp.assign(ts, ts + S);
+  for (size_t s = 0; s < S; ++s) ix->session_to_items_sorted[s].assign(items + off[s], items + off[s + 1]);
+  if (max_len == 0) max_len = exact_p99_5(ix->session_to_items_sorted);
+  prepare_hashmap(*ix, m, max_len, idf_w);
+  return ix;
+}
+
+// VMISIndex::new_from_csv (vmis_index.rs:38-83); max_len == 0 → exact p99.5 (t-digest unpinned)
+void* vo_index_from_csv(const char* path, size_t m, double idf_w, size_t max_len) {
+  Index* ix = new Index();
+  if (!read_from_file(path, *ix)) { delete ix; return nullptr; }
+  if (max_len == 0) max_len = exact_p99_5(ix->session_to_items_sorted);
+  prepare_hashmap(*ix, m, max_len, idf_w);
+  return ix;
+}
+
+void vo_index_free(void* h) { delete (Index*)h; }
+
+size_t vo_num_sessions(const void* h) { return ((const Index*)h)->session_to_items_sorted.size(); }
+size_t vo_num_items(const void* h) { return ((const Index*)h)->item_ids.size(); }
+size_t vo_kept_pairs(const void* h) { return ((const Index*)h)->kept_pairs; }
+size_t vo_max_len(const void* h) { return ((const Index*)h)->max_training_session_length; }
+uint32_t vo_session_ts(const void* h, uint32_t s) { return ((const Index*)h)->session_to_max_time_stamp[s]; }
+
+// items_for_session (vmis_index.rs:317-319): returns length, copies up to cap ids
+size_t vo_items_for_session(const void* h, uint32_t s, uint64_t* buf, size_t cap) {
+  const auto& v = ((const Index*)h)->session_to_items_sorted[s];
+  for (size_t i = 0; i < v.size() && i < cap; ++i) buf[i] = v[i];
+  return v.size();
+}
+// idf (vmis_index.rs:321-323): returns 0 and writes *out if known, -1 if unknown (Rust would panic)
+int vo_idf(const void* h, uint64_t item, double* out) {
+  const Index* ix = (const Index*)h; const uint32_t* s = ix->item_slot.find(item);
+  if (!s) return -1;
+  *out = ix->item_to_idf_score[*s];
+  return 0;
+}
+// postings of an item, time-descending, truncated to m (item_to_top_sessions_ordered)
+size_t vo_postings(const void* h, uint64_t item, uint32_t* buf, size_t cap) {
+  const auto* p = ((const Index*)h)->postings(item); if (!p) return 0;
+  for (size_t i = 0; i < p->size() && i < cap; ++i) buf[i] = (*p)[i];
+  return p->size();
+}
+// attributes: bit0 = exists, bit1 = is_for_sale, bit2 = is_adult
+int vo_find_attributes(const void* h, uint64_t item) {
+  const Attr* a = find_attributes(*(const Index*)h, item); if (!a) return 0;
+  return 1 | (a->is_for_sale ? 2 : 0) | (a->is_adult ? 4 : 0);
+}
+void vo_set_attributes(void* h, uint64_t item, int exists, int for_sale, int adult) {
+  Index* ix = (Index*)h; const uint32_t* s = ix->item_slot.find(item); if (!s) return;
+  ix->item_has_attr[*s] = exists ? 1 : 0; ix->item_to_product_attributes[*s] = Attr{adult != 0, for_sale != 0};
+}
+
+// mode 0 faithful / 1 canonical.  Output order: similarity desc (canonical: + ts desc, sid desc).
+int vo_find_neighbors(const void* h, const uint64_t* ev, size_t L, size_t k, size_t m, int mode,
+                      uint32_t* out_sess, double* out_sim) {
+  const Index& ix = *(const Index*)h;
+  if (mode == 0) {
+    Scratch sc; std::vector<SessionScore> nb; find_neighbors_faithful(ix, ev, L, k, m, sc, nb);
+    DHeap<SessionScore, 2, CmpSessionScore> hp; hp.d = nb; auto v = hp.into_sorted_vec();
+    for (size_t i = 0; i < v.size(); ++i) { out_sess[i] = v[i].id; out_sim[i] = v[i].score; }
+    return (int)v.size();
+  }
+  std::vector<Cand> nb; size_t u = 0; find_neighbors_canonical(ix, ev, L, k, m, nb, &u);
+  for (size_t i = 0; i < nb.size(); ++i) { out_sess[i] = nb[i].sid; out_sim[i] = (double)nb[i].num / (double)u; }
+  return (int)nb.size();
+}
+
+int vo_predict(const void* h, const uint64_t* ev, size_t L, size_t k, size_t m, size_t how_many, int biz, int mode,
+               uint64_t* out_ids, double* out_scores) {
+  const Index& ix = *(const Index*)h; std::vector<ItemScore> out;
+  if (mode == 0) { Scratch sc; std::vector<SessionScore> nb; predict_faithful(ix, ev, L, k, m, how_many, biz != 0, sc, nb, out); }
+  else predict_canonical(ix, ev, L, k, m, how_many, biz != 0, out);
+  for (size_t i = 0; i < out.size(); ++i) { out_ids[i] = out[i].id; out_scores[i] = out[i].score; }
+  return (int)out.size();
+}
+
+// Batch over n_q queries with `threads` worker threads sharing the read-only
+// index (mirrors actix num_workers threads over Arc<VMISIndex>, serving.rs:62-94).
+// Outputs are n_q × how_many, counts per query.  If lat_us != NULL, per-call
+// latency in microseconds is recorded (evaluator.rs:57,66 Stopwatch).  Returns
+// elapsed wall seconds of the query loop.
+double vo_predict_batch(const void* h, const uint64_t* q_items, const uint32_t* q_off, uint32_t n_q,
+                        size_t k, size_t m, size_t how_many, int biz, int mode, int threads,
+                        uint64_t* out_ids, double* out_scores, uint32_t* out_counts, float* lat_us) {
+  const Index& ix = *(const Index*)h;
+  if (threads < 1) threads = 1;
+  std::atomic<uint32_t> next{0};
+  auto t0 = std::chrono::steady_clock::now();
+  auto work = [&]() {
+    Scratch sc; std::vector<SessionScore> nb; std::vector<ItemScore> out;
+    for (;;) {
+      uint32_t lo = next.fetch_add(64); if (lo >= n_q) break;
+      uint32_t hi = std::min(n_q, lo + 64);
+      for (uint32_t q = lo; q < hi; ++q) {
+        const uint64_t* ev = q_items + q_off[q]; size_t L = q_off[q + 1] - q_off[q];
+        auto a = std::chrono::steady_clock::now();
+        if (mode == 0) predict_faithful(ix, ev, L, k, m, how_many, biz != 0, sc, nb, out);
+        else predict_canonical(ix, ev, L, k, m, how_many, biz != 0, out);
+        if (lat_us) lat_us[q] = std::chrono::duration<float, std::micro>(std::chrono::steady_clock::now() - a).count();
+        if (out_counts) out_counts[q] = (uint32_t)out.size();
+        if (out_ids) for (size_t i = 0; i < out.size(); ++i) {
+          out_ids[(size_t)q * how_many + i] = out[i].id; out_scores[(size_t)q * how_many + i] = out[i].score; }
+      }
+    }
+  };
+  std::vector<std::thread> th;
+  for (int t = 1; t < threads; ++t) th.emplace_back(work);
+  work();
+  for (auto& t : th) t.join();
+  return std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
+}
+
+// Heap ordering KATs (mod.rs:313-411) exercised through the restated heaps.
+// which: 0 itemscore top-2, 1 itemscore sorted vec, 2 sessionscore top-2, 3 sessiontime top-2
+int vo_heap_kat(int which, uint64_t* out) {
+  if (which == 0 || which == 2) {
+    const double sc[3] = {5000, 1, 100}; const uint64_t id[3] = {123, 543, 234};
+    DHeap<ItemScore, 2, CmpItemScore> hp;
+    for (int i = 0; i < 3; ++i) {
+      if (hp.size() < 2) hp.push(ItemScore{id[i], sc[i]});
+      else if (sc[i] > hp.top().score) hp.replace_top(ItemScore{id[i], sc[i]});
+    }
+    out[0] = hp.pop().id; out[1] = hp.pop().id; return 2;
+  }
+  if (which == 1) {
+    DHeap<ItemScore, 2, CmpItemScore> hp;
+    hp.push(ItemScore{123, 5000}); hp.push(ItemScore{543, 1}); hp.push(ItemScore{234, 100});
+    auto v = hp.into_sorted_vec(); for (size_t i = 0; i < v.size(); ++i) out[i] = v[i].id; return (int)v.size();
+  }
+  const uint32_t tm[4] = {5000, 99, 1, 499}; const uint32_t id[4] = {123, 345, 456, 234};
+  DHeap<SessionTime, 8, CmpSessionTime> hp;
+  for (int i = 0; i < 4; ++i) {
+    if (hp.size() < 2) hp.push(SessionTime{id[i], tm[i]});
+    else if (tm[i] > hp.top().time) hp.replace_top(SessionTime{id[i], tm[i]});
+  }
+  out[0] = hp.pop().session_id; out[1] = hp.pop().session_id; return 2;
+}
+
+}  // extern "C"
