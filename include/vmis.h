@@ -1,0 +1,167 @@
+/* include/vmis.h — C ABI of the B200-native VMIS-kNN `predict_next` path.
+ *
+ * Drop-in boundary for bolcom/serenade's `src/vmisknn` hot path.  Every entry
+ * point cites the reference interface it replaces (file:line under the
+ * reference tree).  Plain pointers and sizes only; no torch / C++ types.
+ *
+ * Conventions
+ *   - Item ids are the reference's external u64 ids (io.rs:10 `ItemId = u64`).
+ *   - Training session ids are the reference's u32 session indices
+ *     (io.rs:9; position in `session_to_items_sorted`, vmis_index.rs:32).
+ *   - Query batches are CSR: q_items[q_off[q] .. q_off[q+1]) is the evolving
+ *     session of query q, oldest → newest (mod.rs:120 `evolving_session`).
+ *   - All functions returning int return 0 on success, <0 on error; the message
+ *     is available from vmis_last_error() (thread-local).  Nothing aborts the
+ *     process (the reference `unwrap()`s / panics instead — mod.rs:138,157).
+ *   - There is NO CPU fallback: query entry points fail with VMIS_ERR_CUDA if
+ *     no sm_100 device is usable.
+ *   - Query entry points are re-entrant: many host threads may call them
+ *     concurrently on one index (mirrors actix workers sharing Arc<VMISIndex>,
+ *     serving.rs:39,65).
+ */
+#ifndef VMIS_H_
+#define VMIS_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define VMIS_OK 0
+#define VMIS_ERR_ARG (-1)      /* bad argument                                  */
+#define VMIS_ERR_IO (-2)       /* file could not be read / parsed               */
+#define VMIS_ERR_CUDA (-3)     /* CUDA runtime error or no usable device        */
+#define VMIS_ERR_LIMIT (-4)    /* k / m / session length beyond kernel limits   */
+
+/* device ordinal for a host-only handle: the index is built and the trait accessors work, but every
+ * query entry point fails with VMIS_ERR_CUDA (used by CPU-side tests of the builders). */
+#define VMIS_DEVICE_NONE (-1)
+
+/* ProductAttributes (vmis_index.rs:23-26) packed in one byte. */
+#define VMIS_ATTR_EXISTS 1u
+#define VMIS_ATTR_FOR_SALE 2u
+#define VMIS_ATTR_ADULT 4u
+
+typedef struct vmis_index vmis_index_t; /* opaque: host mirror + device CSR arrays (VMISIndex, vmis_index.rs:28-35) */
+
+typedef struct vmis_stats {
+  uint64_t n_sessions;        /* all training sessions (un-pruned, vmis_index.rs:79)   */
+  uint64_t n_sessions_kept;   /* sessions with len <= max_len (vmis_index.rs:452)      */
+  uint64_t n_items;           /* distinct items in kept sessions                       */
+  uint64_t n_pairs_kept;      /* (session,item) pairs kept = idf numerator (:509-512)  */
+  uint64_t n_postings;        /* posting entries after truncation to m (:504)          */
+  uint64_t max_len;           /* max_training_session_length (:67)                     */
+  uint64_t m_build;           /* m_most_recent_sessions used at build                  */
+  uint64_t device_bytes;      /* HBM bytes held by the index                           */
+  double idf_weighting;
+} vmis_stats_t;
+
+/* Per-query work counters written by the kernel when requested (bench: exact
+ * algorithmic bytes per SURVEY.md §8d). */
+typedef struct vmis_query_stats {
+  uint32_t postings_visited;  /* sum_j min(df_j, m) over distinct known items  */
+  uint32_t n_neighbors;       /* |N| <= k                                      */
+  uint32_t neighbor_items;    /* sum of len_s over s in N                      */
+  uint32_t n_out;             /* recommendations written                       */
+} vmis_query_stats_t;
+
+/* ---- construction ------------------------------------------------------- */
+
+/* VMISIndex::new_from_csv(path, m_most_recent_sessions, idf_weighting) — vmis_index.rs:38-83
+ * (read_from_file :591-752 + prepare_hashmap :422-528).  max_training_session_length is the
+ * p99.5 of session lengths as in :67,:715 (t-digest restated).  device = CUDA ordinal. */
+vmis_index_t* vmis_index_from_csv(const char* path, size_t m, double idf_weighting, int device);
+
+/* Same, with max_training_session_length given explicitly (0 = compute p99.5). */
+vmis_index_t* vmis_index_from_csv_ex(const char* path, size_t m, double idf_weighting, size_t max_len, int device);
+
+/* prepare_hashmap(historical_sessions, timestamps, m, max_len, idf_weighting) — vmis_index.rs:422-528,
+ * followed by the VMISIndex{..} assembly of :75-82.  items[sess_off[s]..sess_off[s+1]) are the item ids
+ * of training session s (any order; duplicates not allowed), sess_ts[s] its max timestamp. */
+vmis_index_t* vmis_index_from_sessions(const uint64_t* items, const uint64_t* sess_off, const uint32_t* sess_ts,
+                                       size_t n_sessions, size_t m, size_t max_len, double idf_weighting, int device);
+
+/* item_to_product_attributes (vmis_index.rs:34; Avro fields ForSale/IsAdult :184-192).  Replaces the
+ * attributes of the listed items (flags = VMIS_ATTR_* bits; 0 removes the entry).  Call before serving. */
+int vmis_index_set_attributes(vmis_index_t* index, const uint64_t* items, const uint8_t* flags, size_t n);
+
+void vmis_index_free(vmis_index_t* index);
+
+int vmis_index_stats(const vmis_index_t* index, vmis_stats_t* out);
+
+/* ---- the hot path ------------------------------------------------------- */
+
+/* predict(index, evolving_session, k, m, how_many, enable_business_logic) — mod.rs:118-215, batched.
+ * Host buffers.  out_ids/out_scores are n_q × how_many, row q holds out_counts[q] recommendations in
+ * `into_sorted_vec()` order (score descending, mod.rs:339-355; ties: item id ascending).  An empty evolving
+ * session yields count 0 (the reference panics, mod.rs:157).  stream: cudaStream_t or NULL. */
+int vmis_predict_batch(const vmis_index_t* index, const uint64_t* q_items, const uint32_t* q_off, uint32_t n_q,
+                       uint32_t k, uint32_t m, uint32_t how_many, int enable_business_logic,
+                       uint64_t* out_ids, double* out_scores, uint32_t* out_counts, void* stream);
+
+/* Same computation with every buffer already resident on the index's device (no copies, no sync;
+ * work is enqueued on `stream`).  out_stats may be NULL. */
+int vmis_predict_batch_device(const vmis_index_t* index, const uint64_t* d_q_items, const uint32_t* d_q_off,
+                              uint32_t n_q, uint32_t k, uint32_t m, uint32_t how_many, int enable_business_logic,
+                              uint64_t* d_out_ids, double* d_out_scores, uint32_t* d_out_counts,
+                              vmis_query_stats_t* d_out_stats, void* stream);
+
+/* Single query convenience wrapper over vmis_predict_batch (the exact shape of mod.rs:118-125).
+ * Returns the number of recommendations (>= 0) or a negative error. */
+int vmis_predict(const vmis_index_t* index, const uint64_t* evolving_session, size_t len, size_t k, size_t m,
+                 size_t how_many, int enable_business_logic, uint64_t* out_ids, double* out_scores);
+
+/* SimilarityComputationNew::find_neighbors(evolving_session, k, m) — similarity_indexed.rs:13-22,
+ * vmis_index.rs:325-415, batched.  out_sess/out_sim are n_q × k; row q holds out_counts[q] neighbours ordered
+ * (similarity desc, timestamp desc, session id desc); ids are the reference's session indices. */
+int vmis_find_neighbors_batch(const vmis_index_t* index, const uint64_t* q_items, const uint32_t* q_off,
+                              uint32_t n_q, uint32_t k, uint32_t m, uint32_t* out_sess, double* out_sim,
+                              uint32_t* out_counts, void* stream);
+
+/* ---- trait accessors (host mirror; similarity_indexed.rs:8-24) ---------- */
+
+/* items_for_session(&u32) -> &[u64] — vmis_index.rs:317-319.  Returns a pointer owned by the index
+ * (valid until vmis_index_free) and writes the length; NULL if the session index is out of range. */
+const uint64_t* vmis_items_for_session(const vmis_index_t* index, uint32_t session, size_t* len);
+
+/* idf(&u64) -> f64 — vmis_index.rs:321-323.  0 on success; VMIS_ERR_ARG for an unknown item (reference panics). */
+int vmis_idf(const vmis_index_t* index, uint64_t item, double* out);
+
+/* find_attributes(&u64) -> Option<&ProductAttributes> — vmis_index.rs:417-419.
+ * Returns VMIS_ATTR_* bits; 0 = None. */
+int vmis_find_attributes(const vmis_index_t* index, uint64_t item);
+
+/* item_to_top_sessions_ordered[item] (vmis_index.rs:29): the item's posting list, most recent first,
+ * truncated to m, as reference session indices.  Returns the list length and copies up to cap entries.
+ * Only host-only handles (VMIS_DEVICE_NONE) keep the postings in host memory. */
+size_t vmis_postings(const vmis_index_t* index, uint64_t item, uint32_t* out, size_t cap);
+
+/* session_to_max_time_stamp[session] — vmis_index.rs:30.  0 on success. */
+int vmis_session_timestamp(const vmis_index_t* index, uint32_t session, uint32_t* out);
+
+/* ---- synthetic workloads (BASELINE.json configs 2-5; no counterpart in the reference) ---------------- */
+
+/* Deterministic generator: log-uniform (Zipf s=1) item popularity over n_items sparse u64 ids, session
+ * lengths from the reference's empirical percentiles (vmis_index.rs:116-126, cap 34), items distinct
+ * within a session, one unique u32 timestamp per session.  Call with items == NULL to get the total
+ * number of interactions in *n_interactions; then call again with buffers of that size
+ * (sess_off has n_sessions + 1 entries). */
+int vmis_synth_sessions(uint64_t seed, uint64_t n_items, uint64_t n_sessions, uint64_t* items, uint64_t* sess_off,
+                        uint32_t* sess_ts, uint64_t* n_interactions);
+
+/* Evolving-session queries: a held-out session from the same generator, a random prefix of it, its last
+ * max_items_in_session items (evaluator.rs:46-57).  q_items must hold n_q × max_items_in_session ids. */
+int vmis_synth_queries(uint64_t seed, uint64_t n_items, uint32_t n_q, uint32_t max_items_in_session,
+                       uint64_t* q_items, uint32_t* q_off);
+
+/* ---- misc ---------------------------------------------------------------- */
+
+const char* vmis_last_error(void);
+const char* vmis_version(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* VMIS_H_ */

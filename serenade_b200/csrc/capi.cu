@@ -1,0 +1,381 @@
+// serenade_b200/csrc/capi.cu — the C ABI of include/vmis.h: index handle (host
+// mirror + HBM arrays), pooled per-call contexts (stream, staging buffers, kernel
+// workspace) and the batched entry points.  No CPU fallback anywhere: every query
+// entry point ends in launch_predict() or fails.
+#include <cuda_runtime.h>
+
+#include <algorithm>
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <memory>
+#include <mutex>
+#include <string>
+#include <vector>
+
+#include "vmis_host.h"
+
+namespace {
+
+thread_local std::string g_err;
+
+int fail(int code, const char* fmt, ...) {
+  char buf[512];
+  va_list ap; va_start(ap, fmt); vsnprintf(buf, sizeof buf, fmt, ap); va_end(ap);
+  g_err = buf;
+  return code;
+}
+#define CU_TRY(expr)                                                                     \
+  do {                                                                                   \
+    cudaError_t e__ = (expr);                                                            \
+    if (e__ != cudaSuccess) return fail(VMIS_ERR_CUDA, "%s: %s", #expr, cudaGetErrorString(e__)); \
+  } while (0)
+
+struct CallCtx {
+  cudaStream_t stream = nullptr;
+  cudaEvent_t done = nullptr;      // last use of ws / buf
+  void* buf = nullptr; size_t buf_cap = 0;
+  void* ws = nullptr; size_t ws_cap = 0;
+  ~CallCtx() {
+    if (buf) cudaFree(buf);
+    if (ws) cudaFree(ws);
+    if (done) cudaEventDestroy(done);
+    if (stream) cudaStreamDestroy(stream);
+  }
+};
+
+}  // namespace
+
+struct vmis_index {
+  int device = 0;
+  int sm_count = 0;
+  vmis::Sessions sessions;          // host mirror: session_to_items_sorted / session_to_max_time_stamp
+  vmis::FlatIndex flat;             // item dictionary, idf, attr stay resident for the accessors
+  vmis::IndexView view{};
+  std::vector<void*> dev_allocs;
+  uint64_t device_bytes = 0;
+  uint64_t n_sessions_kept = 0;
+  std::mutex mu;
+  std::vector<std::unique_ptr<CallCtx>> pool;
+};
+
+namespace {
+
+template <class T>
+int upload(vmis_index* ix, const std::vector<T>& v, const T** out) {
+  void* d = nullptr;
+  const size_t bytes = std::max<size_t>(v.size() * sizeof(T), 16);
+  CU_TRY(cudaMalloc(&d, bytes));
+  ix->dev_allocs.push_back(d);
+  ix->device_bytes += bytes;
+  if (!v.empty()) CU_TRY(cudaMemcpy(d, v.data(), v.size() * sizeof(T), cudaMemcpyHostToDevice));
+  *out = static_cast<const T*>(d);
+  return VMIS_OK;
+}
+
+int select_device(int device, int* sm_count) {
+  int n = 0;
+  cudaError_t e = cudaGetDeviceCount(&n);
+  if (e != cudaSuccess || n == 0)
+    return fail(VMIS_ERR_CUDA, "no CUDA device available (%s); this library has no CPU fallback",
+                e == cudaSuccess ? "device count 0" : cudaGetErrorString(e));
+  if (device < 0 || device >= n) return fail(VMIS_ERR_ARG, "device %d out of range [0,%d)", device, n);
+  cudaDeviceProp p;
+  CU_TRY(cudaGetDeviceProperties(&p, device));
+  if (p.major < 10) return fail(VMIS_ERR_CUDA, "device %d is sm_%d%d; kernels are built for sm_100a only", device, p.major, p.minor);
+  CU_TRY(cudaSetDevice(device));
+  *sm_count = p.multiProcessorCount;
+  return VMIS_OK;
+}
+
+vmis_index* finish_index(std::unique_ptr<vmis_index> ix, size_t m, size_t max_len, double idf_w, int device) {
+  std::string err;
+  if (max_len == 0) max_len = vmis::session_length_p99_5(ix->sessions);
+  if (!vmis::build_flat_index(ix->sessions, m, max_len, idf_w, &ix->flat, &err)) { fail(VMIS_ERR_ARG, "%s", err.c_str()); return nullptr; }
+  ix->n_sessions_kept = ix->flat.rank_to_orig.size();
+  ix->device = device;
+  if (device == VMIS_DEVICE_NONE) return ix.release();   // host-only handle: accessors work, queries fail
+  if (select_device(device, &ix->sm_count) != VMIS_OK) return nullptr;
+  vmis::FlatIndex& F = ix->flat;
+  vmis::IndexView& V = ix->view;
+  if (upload(ix.get(), F.item_key, &V.item_key) || upload(ix.get(), F.item_hash, &V.item_hash) ||
+      upload(ix.get(), F.post_ref, &V.post_ref) || upload(ix.get(), F.postings, &V.postings) ||
+      upload(ix.get(), F.sess_ref, &V.sess_ref) || upload(ix.get(), F.sess_items, &V.sess_items) ||
+      upload(ix.get(), F.idf, &V.idf) || upload(ix.get(), F.attr, &V.attr) ||
+      upload(ix.get(), F.rank_to_orig, &V.rank_to_orig)) {
+    for (void* d : ix->dev_allocs) cudaFree(d);
+    return nullptr;
+  }
+  V.item_hash_mask = (uint32_t)F.item_hash.size() - 1;
+  V.n_items = (uint32_t)F.item_key.size();
+  V.n_kept = (uint32_t)F.rank_to_orig.size();
+  V.m_build = F.m_build;
+  V.max_len = F.max_len;
+  // the big CSR arrays now live in HBM only
+  std::vector<uint32_t>().swap(F.postings);
+  std::vector<uint32_t>().swap(F.sess_items);
+  std::vector<uint2>().swap(F.sess_ref);
+  return ix.release();
+}
+
+// borrow a call context; its previous work (possibly on a caller stream) is ordered before ours
+int acquire_ctx(vmis_index* ix, std::unique_ptr<CallCtx>* out) {
+  {
+    std::lock_guard<std::mutex> g(ix->mu);
+    if (!ix->pool.empty()) { *out = std::move(ix->pool.back()); ix->pool.pop_back(); return VMIS_OK; }
+  }
+  std::unique_ptr<CallCtx> c(new CallCtx());
+  CU_TRY(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
+  CU_TRY(cudaEventCreateWithFlags(&c->done, cudaEventDisableTiming));
+  *out = std::move(c);
+  return VMIS_OK;
+}
+void release_ctx(vmis_index* ix, std::unique_ptr<CallCtx> c) {
+  std::lock_guard<std::mutex> g(ix->mu);
+  ix->pool.push_back(std::move(c));
+}
+int ensure(void** p, size_t* cap, size_t need) {
+  if (*cap >= need) return VMIS_OK;
+  if (*p) { CU_TRY(cudaFree(*p)); *p = nullptr; *cap = 0; }
+  need = (need + (size_t(1) << 20)) & ~((size_t(1) << 20) - 1);
+  CU_TRY(cudaMalloc(p, need));
+  *cap = need;
+  return VMIS_OK;
+}
+
+int check_common(const vmis_index* ix, uint32_t k, uint32_t m, vmis::LaunchPlan* plan) {
+  if (!ix) return fail(VMIS_ERR_ARG, "index is NULL");
+  if (ix->device == VMIS_DEVICE_NONE)
+    return fail(VMIS_ERR_CUDA, "host-only index (VMIS_DEVICE_NONE): queries need a B200; there is no CPU fallback");
+  const int rc = vmis::plan_launch(ix->view, k, m, ix->sm_count, plan);
+  if (rc != VMIS_OK)
+    return fail(rc, "k=%u / m=%u beyond kernel limits (k <= %u, m <= %u and shared memory)", k, m, vmis::kMaxK, vmis::kMaxM);
+  return VMIS_OK;
+}
+
+// Enqueue one batch whose buffers are all on the device.
+int run_device(vmis_index* ix, CallCtx* c, const vmis::PredictArgs& args, const vmis::LaunchPlan& plan, cudaStream_t stream) {
+  const int rc = ensure(&c->ws, &c->ws_cap, vmis::workspace_bytes(plan));
+  if (rc) return rc;
+  CU_TRY(cudaStreamWaitEvent(stream, c->done, 0));
+  const vmis::Workspace ws = vmis::carve_workspace(c->ws, plan);
+  CU_TRY(vmis::launch_predict(ix->view, args, plan, ws, stream));
+  CU_TRY(cudaEventRecord(c->done, stream));
+  return VMIS_OK;
+}
+
+int host_batch(const vmis_index* cix, const uint64_t* q_items, const uint32_t* q_off, uint32_t n_q, uint32_t k, uint32_t m,
+               uint32_t how_many, int biz, uint64_t* out_ids, double* out_scores, uint32_t* out_counts,
+               uint32_t* out_sess, double* out_sim, void* stream_) {
+  vmis_index* ix = const_cast<vmis_index*>(cix);
+  vmis::LaunchPlan plan;
+  int rc = check_common(ix, k, m, &plan);
+  if (rc) return rc;
+  if (n_q == 0) return VMIS_OK;
+  if (!q_items || !q_off || !out_counts) return fail(VMIS_ERR_ARG, "NULL query / output buffer");
+  const bool nb_mode = out_sess != nullptr;
+  if (!nb_mode && how_many > 0 && (!out_ids || !out_scores)) return fail(VMIS_ERR_ARG, "NULL output buffer");
+  for (uint32_t q = 0; q < n_q; ++q) {
+    if (q_off[q + 1] < q_off[q]) return fail(VMIS_ERR_ARG, "q_off not monotone at %u", q);
+    if (q_off[q + 1] - q_off[q] > (uint32_t)vmis::kMaxSessionLen)
+      return fail(VMIS_ERR_LIMIT, "evolving session %u has %u items; kernel limit is %d", q, q_off[q + 1] - q_off[q], vmis::kMaxSessionLen);
+  }
+  CU_TRY(cudaSetDevice(ix->device));
+  std::unique_ptr<CallCtx> c;
+  rc = acquire_ctx(ix, &c);
+  if (rc) return rc;
+  cudaStream_t stream = stream_ ? static_cast<cudaStream_t>(stream_) : c->stream;
+  const size_t n_items = q_off[n_q];
+  const size_t width = nb_mode ? k : how_many;
+  auto al = [](size_t x) { return (x + 255) & ~size_t(255); };
+  const size_t o_items = 0, o_off = o_items + al(n_items * 8), o_ids = o_off + al((size_t(n_q) + 1) * 4);
+  const size_t o_sc = o_ids + al(size_t(n_q) * width * 8), o_cnt = o_sc + al(size_t(n_q) * width * 8);
+  const size_t total = o_cnt + al(size_t(n_q) * 4);
+  auto body = [&]() -> int {
+    int r = ensure(&c->buf, &c->buf_cap, total);
+    if (r) return r;
+    unsigned char* b = static_cast<unsigned char*>(c->buf);
+    CU_TRY(cudaStreamWaitEvent(stream, c->done, 0));
+    if (n_items) CU_TRY(cudaMemcpyAsync(b + o_items, q_items, n_items * 8, cudaMemcpyHostToDevice, stream));
+    CU_TRY(cudaMemcpyAsync(b + o_off, q_off, (size_t(n_q) + 1) * 4, cudaMemcpyHostToDevice, stream));
+    vmis::PredictArgs a{};
+    a.q_items = reinterpret_cast<const uint64_t*>(b + o_items);
+    a.q_off = reinterpret_cast<const uint32_t*>(b + o_off);
+    a.n_q = n_q; a.k = k; a.m = m; a.how_many = how_many; a.biz = biz;
+    a.out_counts = reinterpret_cast<uint32_t*>(b + o_cnt);
+    if (nb_mode) { a.out_sess = reinterpret_cast<uint32_t*>(b + o_ids); a.out_sim = reinterpret_cast<double*>(b + o_sc); }
+    else { a.out_ids = reinterpret_cast<uint64_t*>(b + o_ids); a.out_scores = reinterpret_cast<double*>(b + o_sc); }
+    r = run_device(ix, c.get(), a, plan, stream);
+    if (r) return r;
+    if (nb_mode) {
+      if (k) {
+        CU_TRY(cudaMemcpyAsync(out_sess, b + o_ids, size_t(n_q) * k * 4, cudaMemcpyDeviceToHost, stream));
+        CU_TRY(cudaMemcpyAsync(out_sim, b + o_sc, size_t(n_q) * k * 8, cudaMemcpyDeviceToHost, stream));
+      }
+    } else if (how_many) {
+      CU_TRY(cudaMemcpyAsync(out_ids, b + o_ids, size_t(n_q) * how_many * 8, cudaMemcpyDeviceToHost, stream));
+      CU_TRY(cudaMemcpyAsync(out_scores, b + o_sc, size_t(n_q) * how_many * 8, cudaMemcpyDeviceToHost, stream));
+    }
+    CU_TRY(cudaMemcpyAsync(out_counts, b + o_cnt, size_t(n_q) * 4, cudaMemcpyDeviceToHost, stream));
+    CU_TRY(cudaEventRecord(c->done, stream));
+    CU_TRY(cudaStreamSynchronize(stream));
+    return VMIS_OK;
+  };
+  rc = body();
+  release_ctx(ix, std::move(c));
+  return rc;
+}
+
+}  // namespace
+
+extern "C" {
+
+const char* vmis_last_error(void) { return g_err.c_str(); }
+const char* vmis_version(void) { return "serenade_b200 0.1 (sm_100a)"; }
+
+vmis_index_t* vmis_index_from_sessions(const uint64_t* items, const uint64_t* sess_off, const uint32_t* sess_ts,
+                                       size_t n_sessions, size_t m, size_t max_len, double idf_weighting, int device) {
+  if (!sess_off || !sess_ts || (!items && n_sessions && sess_off[n_sessions] > 0)) { fail(VMIS_ERR_ARG, "NULL session arrays"); return nullptr; }
+  std::unique_ptr<vmis_index> ix(new vmis_index());
+  ix->sessions.off.assign(sess_off, sess_off + n_sessions + 1);
+  ix->sessions.ts.assign(sess_ts, sess_ts + n_sessions);
+  ix->sessions.items.assign(items, items + sess_off[n_sessions]);
+  return finish_index(std::move(ix), m, max_len, idf_weighting, device);
+}
+
+vmis_index_t* vmis_index_from_csv_ex(const char* path, size_t m, double idf_weighting, size_t max_len, int device) {
+  if (!path) { fail(VMIS_ERR_ARG, "path is NULL"); return nullptr; }
+  std::unique_ptr<vmis_index> ix(new vmis_index());
+  std::string err;
+  if (!vmis::read_sessions_from_csv(path, &ix->sessions, &err)) { fail(VMIS_ERR_IO, "%s", err.c_str()); return nullptr; }
+  return finish_index(std::move(ix), m, max_len, idf_weighting, device);
+}
+
+vmis_index_t* vmis_index_from_csv(const char* path, size_t m, double idf_weighting, int device) {
+  return vmis_index_from_csv_ex(path, m, idf_weighting, 0, device);
+}
+
+int vmis_index_set_attributes(vmis_index_t* ix, const uint64_t* items, const uint8_t* flags, size_t n) {
+  if (!ix || (n && (!items || !flags))) return fail(VMIS_ERR_ARG, "NULL argument");
+  for (size_t i = 0; i < n; ++i) {
+    const uint32_t d = vmis::host_lookup_item(ix->flat, items[i]);
+    if (d != vmis::kEmpty) ix->flat.attr[d] = flags[i] ? (uint8_t)(flags[i] | VMIS_ATTR_EXISTS) : 0;
+  }
+  if (ix->device == VMIS_DEVICE_NONE) return VMIS_OK;
+  CU_TRY(cudaSetDevice(ix->device));
+  CU_TRY(cudaDeviceSynchronize());
+  if (!ix->flat.attr.empty())
+    CU_TRY(cudaMemcpy(const_cast<uint8_t*>(ix->view.attr), ix->flat.attr.data(), ix->flat.attr.size(), cudaMemcpyHostToDevice));
+  return VMIS_OK;
+}
+
+void vmis_index_free(vmis_index_t* ix) {
+  if (!ix) return;
+  if (ix->device == VMIS_DEVICE_NONE) { delete ix; return; }
+  cudaSetDevice(ix->device);
+  cudaDeviceSynchronize();
+  ix->pool.clear();
+  for (void* d : ix->dev_allocs) cudaFree(d);
+  delete ix;
+}
+
+int vmis_index_stats(const vmis_index_t* ix, vmis_stats_t* out) {
+  if (!ix || !out) return fail(VMIS_ERR_ARG, "NULL argument");
+  out->n_sessions = ix->sessions.size();
+  out->n_sessions_kept = ix->n_sessions_kept;
+  out->n_items = ix->flat.item_key.size();
+  out->n_pairs_kept = ix->flat.n_pairs_kept;
+  out->n_postings = ix->flat.n_postings;
+  out->max_len = ix->flat.max_len;
+  out->m_build = ix->flat.m_build;
+  out->device_bytes = ix->device_bytes;
+  out->idf_weighting = ix->flat.idf_weighting;
+  return VMIS_OK;
+}
+
+int vmis_predict_batch(const vmis_index_t* ix, const uint64_t* q_items, const uint32_t* q_off, uint32_t n_q, uint32_t k,
+                       uint32_t m, uint32_t how_many, int biz, uint64_t* out_ids, double* out_scores,
+                       uint32_t* out_counts, void* stream) {
+  return host_batch(ix, q_items, q_off, n_q, k, m, how_many, biz, out_ids, out_scores, out_counts, nullptr, nullptr, stream);
+}
+
+int vmis_find_neighbors_batch(const vmis_index_t* ix, const uint64_t* q_items, const uint32_t* q_off, uint32_t n_q,
+                              uint32_t k, uint32_t m, uint32_t* out_sess, double* out_sim, uint32_t* out_counts,
+                              void* stream) {
+  if (!out_sess || !out_sim) return fail(VMIS_ERR_ARG, "NULL output buffer");
+  return host_batch(ix, q_items, q_off, n_q, k, m, 0, 0, nullptr, nullptr, out_counts, out_sess, out_sim, stream);
+}
+
+int vmis_predict_batch_device(const vmis_index_t* cix, const uint64_t* d_q_items, const uint32_t* d_q_off, uint32_t n_q,
+                              uint32_t k, uint32_t m, uint32_t how_many, int biz, uint64_t* d_out_ids,
+                              double* d_out_scores, uint32_t* d_out_counts, vmis_query_stats_t* d_out_stats, void* stream_) {
+  vmis_index* ix = const_cast<vmis_index*>(cix);
+  vmis::LaunchPlan plan;
+  int rc = check_common(ix, k, m, &plan);
+  if (rc) return rc;
+  if (n_q == 0) return VMIS_OK;
+  if (!d_q_items || !d_q_off || !d_out_counts || (how_many && (!d_out_ids || !d_out_scores)))
+    return fail(VMIS_ERR_ARG, "NULL device buffer");
+  CU_TRY(cudaSetDevice(ix->device));
+  std::unique_ptr<CallCtx> c;
+  rc = acquire_ctx(ix, &c);
+  if (rc) return rc;
+  cudaStream_t stream = stream_ ? static_cast<cudaStream_t>(stream_) : c->stream;
+  vmis::PredictArgs a{};
+  a.q_items = d_q_items; a.q_off = d_q_off; a.n_q = n_q; a.k = k; a.m = m; a.how_many = how_many; a.biz = biz;
+  a.out_ids = d_out_ids; a.out_scores = d_out_scores; a.out_counts = d_out_counts; a.out_stats = d_out_stats;
+  rc = run_device(ix, c.get(), a, plan, stream);
+  release_ctx(ix, std::move(c));
+  return rc;
+}
+
+int vmis_predict(const vmis_index_t* ix, const uint64_t* ev, size_t len, size_t k, size_t m, size_t how_many, int biz,
+                 uint64_t* out_ids, double* out_scores) {
+  if (len > 0xFFFFFFFFull || k > 0xFFFFFFFFull || m > 0xFFFFFFFFull || how_many > 0xFFFFFFFFull)
+    return fail(VMIS_ERR_ARG, "argument out of range");
+  const uint32_t off[2] = {0u, (uint32_t)len};
+  uint32_t cnt = 0;
+  const int rc = vmis_predict_batch(ix, ev, off, 1, (uint32_t)k, (uint32_t)m, (uint32_t)how_many, biz, out_ids,
+                                    out_scores, &cnt, nullptr);
+  return rc ? rc : (int)cnt;
+}
+
+const uint64_t* vmis_items_for_session(const vmis_index_t* ix, uint32_t session, size_t* len) {
+  if (!ix || session >= ix->sessions.size()) { fail(VMIS_ERR_ARG, "session %u out of range", session); if (len) *len = 0; return nullptr; }
+  if (len) *len = ix->sessions.off[session + 1] - ix->sessions.off[session];
+  return ix->sessions.items.data() + ix->sessions.off[session];
+}
+
+int vmis_idf(const vmis_index_t* ix, uint64_t item, double* out) {
+  if (!ix || !out) return fail(VMIS_ERR_ARG, "NULL argument");
+  const uint32_t d = vmis::host_lookup_item(ix->flat, item);
+  if (d == vmis::kEmpty) return fail(VMIS_ERR_ARG, "unknown item %llu", (unsigned long long)item);
+  *out = ix->flat.idf[d];
+  return VMIS_OK;
+}
+
+int vmis_find_attributes(const vmis_index_t* ix, uint64_t item) {
+  if (!ix) return 0;
+  const uint32_t d = vmis::host_lookup_item(ix->flat, item);
+  if (d == vmis::kEmpty) return 0;
+  const uint8_t a = ix->flat.attr[d];
+  return (a & VMIS_ATTR_EXISTS) ? (int)a : 0;
+}
+
+size_t vmis_postings(const vmis_index_t* ix, uint64_t item, uint32_t* out, size_t cap) {
+  if (!ix) return 0;
+  const uint32_t d = vmis::host_lookup_item(ix->flat, item);
+  if (d == vmis::kEmpty) return 0;
+  const uint2 ref = ix->flat.post_ref[d];
+  if (ix->flat.postings.empty()) { fail(VMIS_ERR_ARG, "postings live in HBM only; use a VMIS_DEVICE_NONE handle to inspect them"); return ref.y; }
+  for (size_t i = 0; i < ref.y && i < cap; ++i) out[i] = ix->flat.rank_to_orig[ix->flat.postings[(size_t)ref.x * 4 + i]];
+  return ref.y;
+}
+
+int vmis_session_timestamp(const vmis_index_t* ix, uint32_t session, uint32_t* out) {
+  if (!ix || !out || session >= ix->sessions.size()) return fail(VMIS_ERR_ARG, "session %u out of range", session);
+  *out = ix->sessions.ts[session];
+  return VMIS_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,280 @@
+// serenade_b200/csrc/index_host.cpp — host-side construction of the VMIS index:
+// TSV reader (read_from_file, vmis_index.rs:591-752), session-length p99.5
+// (vmis_index.rs:693-716) and the CSR builder that replaces prepare_hashmap
+// (vmis_index.rs:422-528) with the flat, time-ranked layout of vmis_device.h.
+#include "vmis_host.h"
+
+#include <algorithm>
+#include <cmath>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <numeric>
+
+namespace vmis {
+namespace {
+
+inline uint64_t mix64(uint64_t x) {
+  x ^= x >> 33; x *= 0xff51afd7ed558ccdull; x ^= x >> 33; x *= 0xc4ceb9fe1a85ec53ull; x ^= x >> 33;
+  return x;
+}
+
+// growable u64 -> u32 map used while building the item dictionary
+struct IdMap {
+  std::vector<uint64_t> keys; std::vector<uint32_t> vals; size_t n = 0, mask = 0;
+  explicit IdMap(size_t cap) { size_t c = 1024; while (c < cap * 2) c <<= 1; keys.assign(c, 0); vals.assign(c, kEmpty); mask = c - 1; }
+  void grow() {
+    std::vector<uint64_t> ok; std::vector<uint32_t> ov; ok.swap(keys); ov.swap(vals);
+    size_t c = (mask + 1) * 2; keys.assign(c, 0); vals.assign(c, kEmpty); mask = c - 1;
+    for (size_t i = 0; i < ov.size(); ++i) if (ov[i] != kEmpty) {
+      size_t h = mix64(ok[i]) & mask; while (vals[h] != kEmpty) h = (h + 1) & mask; keys[h] = ok[i]; vals[h] = ov[i];
+    }
+  }
+  uint32_t get_or_add(uint64_t k) {
+    if ((n + 1) * 2 > mask + 1) grow();
+    size_t h = mix64(k) & mask;
+    while (vals[h] != kEmpty) { if (keys[h] == k) return vals[h]; h = (h + 1) & mask; }
+    keys[h] = k; vals[h] = (uint32_t)n; return (uint32_t)n++;
+  }
+};
+
+// ---- t-digest (merging digest, max_size centroids), the published algorithm of the `tdigest`
+// crate the reference calls at vmis_index.rs:693-716 (TDigest::new_with_size(100).merge_unsorted(v)
+// then estimate_quantile(q)).  The crate is not vendored in the reference tree.
+struct Centroid { double mean, weight; };
+inline double k_to_q(double k, double d) {
+  const double r = k / d;
+  if (r >= 0.5) { const double b = 1.0 - r; return 1.0 - 2.0 * b * b; }
+  return 2.0 * r * r;
+}
+struct TDigest {
+  std::vector<Centroid> c; double count = 0, mn = 0, mx = 0;
+  void merge_sorted(const std::vector<double>& v, size_t max_size) {
+    if (v.empty()) return;
+    count = (double)v.size(); mn = v.front(); mx = v.back();
+    double k_limit = 1.0;
+    double q_limit_times_count = k_to_q(k_limit, (double)max_size) * count; k_limit += 1.0;
+    Centroid curr{v[0], 1.0};
+    double weight_so_far = 1.0, sums = 0.0, weights = 0.0;
+    auto flush = [&](Centroid& x) { const double ns = sums + x.weight * x.mean; const double nw = x.weight + weights;
+                                    x.weight = nw; x.mean = ns / nw; sums = 0.0; weights = 0.0; };
+    for (size_t i = 1; i < v.size(); ++i) {
+      weight_so_far += 1.0;
+      if (weight_so_far <= q_limit_times_count) { sums += v[i]; weights += 1.0; }
+      else {
+        flush(curr); c.push_back(curr);
+        q_limit_times_count = k_to_q(k_limit, (double)max_size) * count; k_limit += 1.0;
+        curr = Centroid{v[i], 1.0};
+      }
+    }
+    flush(curr); c.push_back(curr);
+    std::stable_sort(c.begin(), c.end(), [](const Centroid& a, const Centroid& b) { return a.mean < b.mean; });
+  }
+  double estimate_quantile(double q) const {
+    if (c.empty()) return 0.0;
+    const double rank = q * count; size_t pos; double t;
+    if (q > 0.5) {
+      if (q >= 1.0) return mx;
+      pos = 0; t = count;
+      for (size_t k = c.size(); k-- > 0;) { t -= c[k].weight; if (rank >= t) { pos = k; break; } }
+    } else {
+      if (q <= 0.0) return mn;
+      pos = c.size() - 1; t = 0.0;
+      for (size_t k = 0; k < c.size(); ++k) { if (rank < t + c[k].weight) { pos = k; break; } t += c[k].weight; }
+    }
+    double delta = 0.0, lo = mn, hi = mx;
+    if (c.size() > 1) {
+      if (pos == 0) { delta = c[1].mean - c[0].mean; hi = c[1].mean; }
+      else if (pos == c.size() - 1) { delta = c[pos].mean - c[pos - 1].mean; lo = c[pos - 1].mean; }
+      else { delta = (c[pos + 1].mean - c[pos - 1].mean) / 2.0; lo = c[pos - 1].mean; hi = c[pos + 1].mean; }
+    }
+    const double value = c[pos].mean + ((rank - t) / c[pos].weight - 0.5) * delta;
+    return std::min(std::max(value, lo), hi);
+  }
+};
+
+}  // namespace
+
+size_t session_length_p99_5(const Sessions& s) {
+  std::vector<double> lens(s.size());
+  for (size_t i = 0; i < s.size(); ++i) lens[i] = (double)(s.off[i + 1] - s.off[i]);
+  std::sort(lens.begin(), lens.end());
+  TDigest d; d.merge_sorted(lens, 100);
+  return (size_t)std::llround(d.estimate_quantile(0.995));
+}
+
+bool read_sessions_from_csv(const std::string& path, Sessions* out, std::string* err) {
+  FILE* f = std::fopen(path.c_str(), "rb");
+  if (!f) { *err = "cannot open " + path; return false; }
+  struct Row { uint64_t session, item, time; };
+  std::vector<Row> rows;
+  char line[8192];
+  bool first = true;
+  size_t bad = 0;
+  while (std::fgets(line, sizeof line, f)) {
+    if (first) { first = false; continue; }                         // header row (:597)
+    char* e = nullptr; const char* p = line;
+    if (*p == '\n' || *p == '\r' || *p == 0) continue;
+    const unsigned long long sid = std::strtoull(p, &e, 10);
+    if (e == p || *e != '\t') { ++bad; continue; }
+    p = e + 1; const unsigned long long iid = std::strtoull(p, &e, 10);
+    if (e == p || *e != '\t') { ++bad; continue; }
+    p = e + 1; const double t = std::strtod(p, &e);
+    if (e == p) { ++bad; continue; }
+    rows.push_back(Row{sid, iid, (uint64_t)std::llround(t)});        // (usize, usize, f64.round()) :607-609
+  }
+  std::fclose(f);
+  if (bad) std::fprintf(stderr, "vmis: %zu unparsable rows skipped in %s\n", bad, path.c_str());
+  if (rows.empty()) { *err = "no rows in " + path; return false; }
+  // rows grouped by session id, file order kept inside a session (stable, :620-633)
+  std::stable_sort(rows.begin(), rows.end(), [](const Row& a, const Row& b) { return a.session < b.session; });
+  const size_t n = rows.size();
+  out->items.clear(); out->off.assign(1, 0); out->ts.clear();
+  std::vector<uint64_t> cur; cur.push_back(rows[0].item);
+  uint64_t max_ts = rows[0].time;
+  auto close_session = [&]() {
+    std::sort(cur.begin(), cur.end());                               // items ascending (:676-678)
+    out->items.insert(out->items.end(), cur.begin(), cur.end());
+    out->off.push_back(out->items.size());
+    out->ts.push_back((uint32_t)max_ts);
+  };
+  for (size_t i = 1; i < n; ++i) {
+    // The reference closes the running session at a session change AND at the very last row, whose
+    // own item is then dropped (:666-667, :675-686).  Reproduced on purpose.
+    const bool same = rows[i].session == rows[i - 1].session && i != n - 1;
+    if (same) {
+      if (std::find(cur.begin(), cur.end(), rows[i].item) == cur.end()) {   // first occurrence only (:668)
+        cur.push_back(rows[i].item);
+        if (rows[i].time > max_ts) max_ts = rows[i].time;             // only non-duplicate rows move the clock (:671)
+      }
+    } else {
+      close_session();
+      cur.clear(); cur.push_back(rows[i].item); max_ts = rows[i].time;
+    }
+  }
+  return true;
+}
+
+uint32_t host_lookup_item(const FlatIndex& f, uint64_t item) {
+  if (f.item_hash.empty()) return kEmpty;
+  const uint32_t mask = (uint32_t)f.item_hash.size() - 1;
+  uint32_t h = (uint32_t)mix64(item) & mask;
+  for (;;) {
+    const ItemHashEntry& e = f.item_hash[h];
+    if (e.val == kEmpty) return kEmpty;
+    if (e.key == item) return e.val;
+    h = (h + 1) & mask;
+  }
+}
+
+bool build_flat_index(const Sessions& s, size_t m, size_t max_len, double idf_weighting, FlatIndex* out,
+                      std::string* err) {
+  const size_t S = s.size();
+  if (S >= 0xFFFFFFFFull) { *err = "too many sessions"; return false; }
+  if (m == 0) { *err = "m must be >= 1"; return false; }
+  FlatIndex& F = *out;
+  F = FlatIndex();
+  F.m_build = (uint32_t)std::min<size_t>(m, 0xFFFFFFFFu);
+  F.max_len = (uint32_t)std::min<size_t>(max_len, 0xFFFFFFFFu);
+  F.idf_weighting = idf_weighting;
+
+  // 1. kept sessions (len <= max_len, :452) ranked by (timestamp, session idx) ascending.  The rank
+  //    replaces the timestamp: "more recent" == "larger rank", ties broken like the stable sort +
+  //    reverse of :497-503 (higher session idx first).
+  std::vector<uint64_t> order; order.reserve(S);
+  uint64_t P = 0;
+  for (size_t i = 0; i < S; ++i) {
+    const uint64_t len = s.off[i + 1] - s.off[i];
+    if (len <= max_len && len > 0) { order.push_back(((uint64_t)s.ts[i] << 32) | (uint64_t)i); P += len; }
+  }
+  std::sort(order.begin(), order.end());
+  const size_t Sk = order.size();
+  F.rank_to_orig.resize(Sk);
+  for (size_t r = 0; r < Sk; ++r) F.rank_to_orig[r] = (uint32_t)(order[r] & 0xFFFFFFFFull);
+  F.n_pairs_kept = P;
+
+  // 2. item dictionary: temp ids in first-seen order, document frequencies
+  IdMap ids(1 << 16);
+  std::vector<uint32_t> entry_tid(P);
+  std::vector<uint32_t> df;
+  {
+    size_t e = 0;
+    for (size_t r = 0; r < Sk; ++r) {
+      const uint32_t o = F.rank_to_orig[r];
+      for (uint64_t p = s.off[o]; p < s.off[o + 1]; ++p) {
+        const uint32_t t = ids.get_or_add(s.items[p]);
+        if (t == df.size()) df.push_back(0);
+        ++df[t]; entry_tid[e++] = t;
+      }
+    }
+  }
+  const size_t I = df.size();
+  std::vector<uint64_t> tkey(I);
+  for (size_t h = 0; h <= ids.mask; ++h) if (ids.vals[h] != kEmpty) tkey[ids.vals[h]] = ids.keys[h];
+  std::vector<uint32_t> by_key(I); std::iota(by_key.begin(), by_key.end(), 0u);
+  std::sort(by_key.begin(), by_key.end(), [&](uint32_t a, uint32_t b) { return tkey[a] < tkey[b]; });
+  std::vector<uint32_t> dense_of_temp(I);
+  F.item_key.resize(I);
+  for (size_t d = 0; d < I; ++d) { dense_of_temp[by_key[d]] = (uint32_t)d; F.item_key[d] = tkey[by_key[d]]; }
+
+  // 3. session -> items (dense, ascending), 16-byte aligned starts
+  F.sess_ref.resize(Sk);
+  F.sess_items.clear(); F.sess_items.reserve(P + P / 3 + 16);
+  {
+    size_t e = 0; std::vector<uint32_t> tmp;
+    for (size_t r = 0; r < Sk; ++r) {
+      const uint32_t o = F.rank_to_orig[r];
+      const uint32_t len = (uint32_t)(s.off[o + 1] - s.off[o]);
+      tmp.resize(len);
+      for (uint32_t t = 0; t < len; ++t) tmp[t] = dense_of_temp[entry_tid[e + t]];
+      std::sort(tmp.begin(), tmp.end());
+      for (uint32_t t = 1; t < len; ++t) if (tmp[t] == tmp[t - 1]) { *err = "duplicate item inside a training session"; return false; }
+      const size_t start = F.sess_items.size();
+      if ((start >> 2) > 0xFFFFFFFFull) { *err = "session item array too large"; return false; }
+      F.sess_ref[r] = make_uint2((uint32_t)(start >> 2), len);
+      F.sess_items.insert(F.sess_items.end(), tmp.begin(), tmp.end());
+      while (F.sess_items.size() & 3) F.sess_items.push_back(kEmpty);
+      e += len;
+    }
+  }
+  std::vector<uint32_t>().swap(entry_tid);
+
+  // 4. postings: per item the min(df, m) most recent kept sessions, rank descending (:497-504)
+  F.post_ref.resize(I);
+  {
+    uint64_t pos = 0;
+    for (size_t d = 0; d < I; ++d) {
+      const uint32_t len = (uint32_t)std::min<uint64_t>(df[by_key[d]], m);
+      if ((pos >> 2) > 0xFFFFFFFFull) { *err = "posting array too large"; return false; }
+      F.post_ref[d] = make_uint2((uint32_t)(pos >> 2), len);
+      F.n_postings += len;
+      pos += (len + 3u) & ~3u;
+    }
+    F.postings.assign(pos, kEmpty);
+    std::vector<uint32_t> fill(I, 0);
+    for (size_t r = Sk; r-- > 0;) {
+      const uint2 ref = F.sess_ref[r];
+      const uint32_t* it = &F.sess_items[(size_t)ref.x * 4];
+      for (uint32_t t = 0; t < ref.y; ++t) {
+        const uint32_t d = it[t];
+        if (fill[d] < F.post_ref[d].y) F.postings[(size_t)F.post_ref[d].x * 4 + fill[d]++] = (uint32_t)r;
+      }
+    }
+  }
+
+  // 5. idf = ln(P_kept / df) * idf_weighting (:509-513); default attributes (:514-518)
+  F.idf.resize(I); F.attr.assign(I, (uint8_t)(VMIS_ATTR_EXISTS | VMIS_ATTR_FOR_SALE));
+  for (size_t d = 0; d < I; ++d) F.idf[d] = std::log((double)P / (double)df[by_key[d]]) * idf_weighting;
+
+  // 6. device item hash
+  size_t cap = 16; while (cap < I * 2) cap <<= 1;
+  F.item_hash.assign(cap, ItemHashEntry{0, kEmpty, 0});
+  for (size_t d = 0; d < I; ++d) {
+    uint32_t h = (uint32_t)mix64(F.item_key[d]) & (uint32_t)(cap - 1);
+    while (F.item_hash[h].val != kEmpty) h = (h + 1) & (uint32_t)(cap - 1);
+    F.item_hash[h] = ItemHashEntry{F.item_key[d], (uint32_t)d, 0};
+  }
+  return true;
+}
+
+}  // namespace vmis

@@ -1,0 +1,100 @@
+// serenade_b200/csrc/vmis_device.h — device-side view of the VMIS index and the
+// launch interface of the sm_100a predict kernel.  Internal header (the public
+// boundary is include/vmis.h).
+#pragma once
+#include <cstdint>
+#include <cuda_runtime.h>
+
+#include "../../include/vmis.h"
+
+namespace vmis {
+
+constexpr uint32_t kEmpty = 0xFFFFFFFFu;
+constexpr int kThreads = 256;            // one CTA per evolving session
+constexpr int kWarps = kThreads / 32;
+constexpr int kMaxSessionLen = 128;      // evolving-session length limit of the kernel (reference HPO grid: <= 100)
+constexpr uint32_t kMaxK = 2048;         // keeps the int32 item numerators exact
+constexpr uint32_t kMaxM = 8192;         // shared-memory bound of the m-sample buffers
+
+// ext item id -> dense item index; open addressing, val == kEmpty marks a free slot
+struct alignas(16) ItemHashEntry {
+  uint64_t key;
+  uint32_t val;
+  uint32_t pad;
+};
+
+// HBM layout (all arrays immutable after build):
+//   item dictionary   item_key[I] ascending external ids; dense index = rank, so
+//                     (score desc, dense idx asc) == (score desc, item_id asc)
+//   postings          per item: kept-session TIME RANKS, descending (most recent first),
+//                     truncated to m_build, list start aligned to 16 B
+//                     (replaces item_to_top_sessions_ordered + the session_to_max_time_stamp
+//                     gather of vmis_index.rs:359: rank order == (ts, session idx) order)
+//   sess_items        per kept session (by time rank): dense item indices ascending,
+//                     list start aligned to 16 B (replaces session_to_items_sorted)
+//   idf[I], attr[I]   item_to_idf_score / item_to_product_attributes
+//   rank_to_orig[Sk]  time rank -> reference session index (find_neighbors output only)
+struct IndexView {
+  const uint64_t* item_key;
+  const ItemHashEntry* item_hash;
+  uint32_t item_hash_mask;
+  const uint2* post_ref;      // {offset in units of 4 entries, length}
+  const uint32_t* postings;
+  const uint2* sess_ref;      // {offset in units of 4 entries, length}
+  const uint32_t* sess_items;
+  const double* idf;
+  const uint8_t* attr;
+  const uint32_t* rank_to_orig;
+  uint32_t n_items;
+  uint32_t n_kept;
+  uint32_t m_build;
+  uint32_t max_len;
+};
+
+struct PredictArgs {
+  const uint64_t* q_items;    // device
+  const uint32_t* q_off;      // device, n_q + 1
+  uint32_t n_q;
+  uint32_t k, m, how_many;
+  int biz;
+  // outputs (device); predict mode
+  uint64_t* out_ids;
+  double* out_scores;
+  uint32_t* out_counts;
+  vmis_query_stats_t* out_stats;  // optional
+  // find_neighbors mode (out_sess != nullptr): rows of k
+  uint32_t* out_sess;
+  double* out_sim;
+};
+
+// Persistent-CTA workspace owned by the caller: a work counter plus one global
+// overflow score table per resident CTA.
+struct Workspace {
+  uint32_t* counter;          // 1 × u32, zeroed by the launcher
+  uint32_t* gtab_keys;        // grid × gtab_cap
+  int32_t* gtab_vals;         // grid × gtab_cap
+  uint32_t gtab_cap;          // power of two >= 2 * k * max_len
+  uint32_t grid;
+};
+
+struct LaunchPlan {
+  uint32_t grid;
+  uint32_t smem_bytes;
+  uint32_t tab_cap;           // shared score table slots (power of two)
+  uint32_t m_eff;             // acc buffer capacity
+  uint32_t list_cap;          // posting staging capacity
+  uint32_t gtab_cap;
+};
+
+// Computes launch geometry; returns VMIS_OK or VMIS_ERR_LIMIT.
+int plan_launch(const IndexView& ix, uint32_t k, uint32_t m, int sm_count, LaunchPlan* plan);
+size_t workspace_bytes(const LaunchPlan& plan);
+// carve a raw device allocation of workspace_bytes() into a Workspace
+Workspace carve_workspace(void* base, const LaunchPlan& plan);
+// Enqueues counter reset + the predict kernel on `stream`.
+cudaError_t launch_predict(const IndexView& ix, const PredictArgs& args, const LaunchPlan& plan, const Workspace& ws,
+                           cudaStream_t stream);
+// number of kernels launch_predict enqueues (bench "gpu_launches")
+constexpr int kLaunchesPerBatch = 1;
+
+}  // namespace vmis

@@ -1,0 +1,248 @@
+"""ctypes binding of include/vmis.h, shaped like the reference's Rust surface.
+
+Reference interface mirrored here (file:line under the reference tree):
+  * ``VMISIndex::new_from_csv``            src/vmisknn/vmis_index.rs:38
+  * trait ``SimilarityComputationNew``     src/vmisknn/similarity_indexed.rs:8-24
+      ``items_for_session``, ``idf``, ``find_neighbors``, ``find_attributes``
+  * ``vmisknn::predict``                   src/vmisknn/mod.rs:118-125
+
+There is no CPU implementation behind these calls: if ``libvmis_b200.so`` is missing the
+import of the library fails loudly, and every query needs a B200 (sm_100) device.
+"""
+import ctypes as C
+import os
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+_LIB_PATH = os.path.join(_HERE, "libvmis_b200.so")
+
+DEVICE_NONE = -1
+ATTR_EXISTS, ATTR_FOR_SALE, ATTR_ADULT = 1, 2, 4
+
+
+class VmisError(RuntimeError):
+    def __init__(self, code, msg):
+        super().__init__(f"vmis error {code}: {msg}")
+        self.code = code
+
+
+class _Stats(C.Structure):
+    _fields_ = [(n, C.c_uint64) for n in ("n_sessions", "n_sessions_kept", "n_items", "n_pairs_kept", "n_postings",
+                                          "max_len", "m_build", "device_bytes")] + [("idf_weighting", C.c_double)]
+
+
+_lib = None
+_u64p, _u32p, _f64p, _u8p = C.POINTER(C.c_uint64), C.POINTER(C.c_uint32), C.POINTER(C.c_double), C.POINTER(C.c_uint8)
+
+
+def load_library():
+    """Load libvmis_b200.so (built by ``__graft_entry__.build()`` / ``make -C serenade_b200/csrc``)."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(_LIB_PATH):
+        raise ImportError(f"{_LIB_PATH} is missing: build it with `make -C serenade_b200/csrc` "
+                          "(there is no Python/CPU fallback for the VMIS-kNN kernels)")
+    L = C.CDLL(_LIB_PATH)
+    vp, sz, i32, u32, u64, f64 = C.c_void_p, C.c_size_t, C.c_int, C.c_uint32, C.c_uint64, C.c_double
+    sig = {
+        "vmis_index_from_csv": (vp, [C.c_char_p, sz, f64, i32]),
+        "vmis_index_from_csv_ex": (vp, [C.c_char_p, sz, f64, sz, i32]),
+        "vmis_index_from_sessions": (vp, [_u64p, _u64p, _u32p, sz, sz, sz, f64, i32]),
+        "vmis_index_set_attributes": (i32, [vp, _u64p, _u8p, sz]),
+        "vmis_index_free": (None, [vp]),
+        "vmis_index_stats": (i32, [vp, C.POINTER(_Stats)]),
+        "vmis_predict_batch": (i32, [vp, _u64p, _u32p, u32, u32, u32, u32, i32, _u64p, _f64p, _u32p, vp]),
+        "vmis_predict_batch_device": (i32, [vp, vp, vp, u32, u32, u32, u32, i32, vp, vp, vp, vp, vp]),
+        "vmis_predict": (i32, [vp, _u64p, sz, sz, sz, sz, i32, _u64p, _f64p]),
+        "vmis_find_neighbors_batch": (i32, [vp, _u64p, _u32p, u32, u32, u32, _u32p, _f64p, _u32p, vp]),
+        "vmis_items_for_session": (_u64p, [vp, u32, C.POINTER(sz)]),
+        "vmis_idf": (i32, [vp, u64, _f64p]),
+        "vmis_find_attributes": (i32, [vp, u64]),
+        "vmis_postings": (sz, [vp, u64, _u32p, sz]),
+        "vmis_session_timestamp": (i32, [vp, u32, _u32p]),
+        "vmis_synth_sessions": (i32, [u64, u64, u64, _u64p, _u64p, _u32p, _u64p]),
+        "vmis_synth_queries": (i32, [u64, u64, u32, u32, _u64p, _u32p]),
+        "vmis_last_error": (C.c_char_p, []),
+        "vmis_version": (C.c_char_p, []),
+    }
+    for name, (res, args) in sig.items():
+        fn = getattr(L, name)
+        fn.restype, fn.argtypes = res, args
+    _lib = L
+    return L
+
+
+EXPORTED_SYMBOLS = ("vmis_index_from_csv", "vmis_index_from_csv_ex", "vmis_index_from_sessions",
+                    "vmis_index_set_attributes", "vmis_index_free", "vmis_index_stats", "vmis_predict_batch",
+                    "vmis_predict_batch_device", "vmis_predict", "vmis_find_neighbors_batch", "vmis_items_for_session",
+                    "vmis_idf", "vmis_find_attributes", "vmis_postings", "vmis_session_timestamp",
+                    "vmis_synth_sessions", "vmis_synth_queries", "vmis_last_error", "vmis_version")
+
+
+def _check(rc):
+    if rc < 0:
+        raise VmisError(rc, load_library().vmis_last_error().decode())
+    return rc
+
+
+def _p(a, t):
+    return a.ctypes.data_as(C.POINTER(t))
+
+
+def _csr(sessions):
+    """list of item lists -> (items u64, off u32)"""
+    lens = np.fromiter((len(s) for s in sessions), dtype=np.int64, count=len(sessions))
+    off = np.zeros(len(sessions) + 1, dtype=np.uint32)
+    np.cumsum(lens, out=off[1:])
+    items = np.fromiter((int(i) for s in sessions for i in s), dtype=np.uint64, count=int(off[-1]))
+    return items, off
+
+
+class VMISIndex:
+    """``VMISIndex`` (vmis_index.rs:28-35) resident in HBM; implements ``SimilarityComputationNew``."""
+
+    def __init__(self, handle):
+        if not handle:
+            raise VmisError(-1, load_library().vmis_last_error().decode())
+        self._h = C.c_void_p(handle)
+
+    # -- constructors -------------------------------------------------------------------------------
+    @classmethod
+    def new_from_csv(cls, path_to_training, m_most_recent_sessions, idf_weighting, max_len=0, device=0):
+        """vmis_index.rs:38 (max_len=0 → p99.5 of the session lengths, :67)."""
+        L = load_library()
+        return cls(L.vmis_index_from_csv_ex(os.fsencode(path_to_training), m_most_recent_sessions,
+                                            float(idf_weighting), max_len, device))
+
+    @classmethod
+    def from_sessions(cls, items, sess_off, sess_ts, m_most_recent_sessions, max_len, idf_weighting, device=0):
+        """prepare_hashmap (vmis_index.rs:422) + struct assembly (:75-82)."""
+        L = load_library()
+        items = np.ascontiguousarray(items, dtype=np.uint64)
+        sess_off = np.ascontiguousarray(sess_off, dtype=np.uint64)
+        sess_ts = np.ascontiguousarray(sess_ts, dtype=np.uint32)
+        return cls(L.vmis_index_from_sessions(_p(items, C.c_uint64), _p(sess_off, C.c_uint64),
+                                              _p(sess_ts, C.c_uint32), len(sess_ts), m_most_recent_sessions, max_len,
+                                              float(idf_weighting), device))
+
+    def close(self):
+        if getattr(self, "_h", None) and _lib is not None:
+            _lib.vmis_index_free(self._h)
+        self._h = None
+
+    __del__ = close
+
+    @property
+    def handle(self):
+        return self._h
+
+    def stats(self):
+        st = _Stats()
+        _check(load_library().vmis_index_stats(self._h, C.byref(st)))
+        return {n: getattr(st, n) for n, _ in _Stats._fields_}
+
+    def set_attributes(self, items, flags):
+        items = np.ascontiguousarray(items, dtype=np.uint64)
+        flags = np.ascontiguousarray(flags, dtype=np.uint8)
+        _check(load_library().vmis_index_set_attributes(self._h, _p(items, C.c_uint64), _p(flags, C.c_uint8),
+                                                        len(items)))
+
+    # -- trait SimilarityComputationNew ---------------------------------------------------------------
+    def items_for_session(self, session_idx):
+        n = C.c_size_t()
+        ptr = load_library().vmis_items_for_session(self._h, session_idx, C.byref(n))
+        if not ptr:
+            raise IndexError(session_idx)
+        return np.ctypeslib.as_array(ptr, shape=(n.value,)).copy() if n.value else np.zeros(0, np.uint64)
+
+    def idf(self, item_id):
+        out = C.c_double()
+        if load_library().vmis_idf(self._h, int(item_id), C.byref(out)) != 0:
+            raise KeyError(item_id)   # the reference panics (vmis_index.rs:322)
+        return out.value
+
+    def find_attributes(self, item_id):
+        a = load_library().vmis_find_attributes(self._h, int(item_id))
+        return None if not (a & ATTR_EXISTS) else {"is_for_sale": bool(a & ATTR_FOR_SALE),
+                                                    "is_adult": bool(a & ATTR_ADULT)}
+
+    def postings(self, item_id, cap=1 << 16):
+        buf = np.zeros(cap, dtype=np.uint32)
+        n = load_library().vmis_postings(self._h, int(item_id), _p(buf, C.c_uint32), cap)
+        return buf[:min(n, cap)].copy()
+
+    def session_timestamp(self, session_idx):
+        out = C.c_uint32()
+        _check(load_library().vmis_session_timestamp(self._h, session_idx, C.byref(out)))
+        return out.value
+
+    def find_neighbors(self, evolving_session, k, m):
+        """-> (session ids, similarities), best first (vmis_index.rs:325-415)."""
+        sess, sim, cnt = self.find_neighbors_batch([evolving_session], k, m)
+        return sess[0, :cnt[0]].copy(), sim[0, :cnt[0]].copy()
+
+    def find_neighbors_batch(self, sessions, k, m):
+        q_items, q_off = sessions if isinstance(sessions, tuple) else _csr(sessions)
+        n_q = len(q_off) - 1
+        sess = np.zeros((n_q, max(k, 1)), dtype=np.uint32)
+        sim = np.zeros((n_q, max(k, 1)), dtype=np.float64)
+        cnt = np.zeros(n_q, dtype=np.uint32)
+        _check(load_library().vmis_find_neighbors_batch(self._h, _p(q_items, C.c_uint64), _p(q_off, C.c_uint32), n_q,
+                                                        k, m, _p(sess, C.c_uint32), _p(sim, C.c_double),
+                                                        _p(cnt, C.c_uint32), None))
+        return sess, sim, cnt
+
+
+def predict_batch(index, sessions, k, m, how_many, enable_business_logic=False, out=None, stream=None):
+    """Batched ``predict``: sessions is a list of item-id lists or a CSR pair (q_items u64, q_off u32).
+    Returns (ids [n_q, how_many] u64, scores f64, counts u32)."""
+    q_items, q_off = sessions if isinstance(sessions, tuple) else _csr(sessions)
+    q_items = np.ascontiguousarray(q_items, dtype=np.uint64)
+    q_off = np.ascontiguousarray(q_off, dtype=np.uint32)
+    n_q = len(q_off) - 1
+    if out is None:
+        ids = np.zeros((n_q, max(how_many, 1)), dtype=np.uint64)
+        sc = np.zeros((n_q, max(how_many, 1)), dtype=np.float64)
+        cnt = np.zeros(n_q, dtype=np.uint32)
+    else:
+        ids, sc, cnt = out
+    _check(load_library().vmis_predict_batch(index.handle, _p(q_items, C.c_uint64), _p(q_off, C.c_uint32), n_q, k, m,
+                                             how_many, int(enable_business_logic), _p(ids, C.c_uint64),
+                                             _p(sc, C.c_double), _p(cnt, C.c_uint32), stream))
+    return ids, sc, cnt
+
+
+def predict(index, evolving_session, k, m, how_many, enable_business_logic=False):
+    """``vmisknn::predict`` (mod.rs:118-125) → list of (item_id, score), score-descending — the order of
+    ``recommendations.into_sorted_vec()`` at the reference call sites (recommend_resource.rs:58-62)."""
+    ev = np.ascontiguousarray(evolving_session, dtype=np.uint64)
+    ids = np.zeros(max(how_many, 1), dtype=np.uint64)
+    sc = np.zeros(max(how_many, 1), dtype=np.float64)
+    n = _check(load_library().vmis_predict(index.handle, _p(ev, C.c_uint64), len(ev), k, m, how_many,
+                                           int(enable_business_logic), _p(ids, C.c_uint64), _p(sc, C.c_double)))
+    return [(int(ids[i]), float(sc[i])) for i in range(n)]
+
+
+def synth_sessions(seed, n_items, n_sessions):
+    """Synthetic training sessions → (items u64, sess_off u64, sess_ts u32)."""
+    L = load_library()
+    total = C.c_uint64()
+    _check(L.vmis_synth_sessions(seed, n_items, n_sessions, None, None, None, C.byref(total)))
+    items = np.empty(total.value, dtype=np.uint64)
+    off = np.empty(n_sessions + 1, dtype=np.uint64)
+    ts = np.empty(n_sessions, dtype=np.uint32)
+    _check(L.vmis_synth_sessions(seed, n_items, n_sessions, _p(items, C.c_uint64), _p(off, C.c_uint64),
+                                 _p(ts, C.c_uint32), C.byref(total)))
+    return items, off, ts
+
+
+def synth_queries(seed, n_items, n_q, max_items_in_session=4):
+    """Synthetic evolving sessions (evaluator.rs:46-57 shape) → CSR (q_items u64, q_off u32)."""
+    L = load_library()
+    q_items = np.empty(n_q * max_items_in_session, dtype=np.uint64)
+    q_off = np.empty(n_q + 1, dtype=np.uint32)
+    _check(L.vmis_synth_queries(seed, n_items, n_q, max_items_in_session, _p(q_items, C.c_uint64),
+                                _p(q_off, C.c_uint32)))
+    return q_items[:q_off[-1]].copy(), q_off

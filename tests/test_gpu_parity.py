@@ -1,0 +1,248 @@
+"""Parity of the sm_100a kernel (through the C ABI) against the CPU oracle.  Needs a B200."""
+import ctypes as C
+import os
+
+import numpy as np
+import pytest
+
+from util import csr, evaluator_queries, random_index_data, read_test_sessions, same_modulo_ties
+
+pytestmark = pytest.mark.gpu
+
+README_13598 = [2835, 10, 12068, 4313, 3097, 8028, 3545, 7812, 17519, 1164, 17935, 1277, 13335, 8655, 14664, 14556,
+                6868, 13509, 9248, 2498, 11724]
+
+
+def _assert_batch_equal(sb, gix, oix, queries, k, m, n, biz=False):
+    """GPU vs canonical oracle: ids bit-exact and in the same order, f64 scores bit-exact."""
+    ids, sc, cnt = sb.predict_batch(gix, queries, k, m, n, biz)
+    q_items, q_off = csr(queries)
+    oids, osc, ocnt, _, _ = oix.predict_batch(q_items, q_off, k, m, n, biz, mode=1)
+    assert np.array_equal(cnt, ocnt), f"counts differ at {np.nonzero(cnt != ocnt)[0][:10]}"
+    for q in range(len(queries)):
+        c = cnt[q]
+        if not np.array_equal(ids[q, :c], oids[q, :c]) or not np.array_equal(sc[q, :c], osc[q, :c]):
+            raise AssertionError(f"query {q} {queries[q]} k={k} m={m} n={n}:\n gpu {ids[q, :c]} {sc[q, :c]}\n"
+                                 f" ora {oids[q, :c]} {osc[q, :c]}")
+    return ids, sc, cnt
+
+
+@pytest.fixture(scope="module")
+def toy(sb, oracle, toy_dir):
+    train = os.path.join(toy_dir, "train.txt")
+    gix = sb.VMISIndex.new_from_csv(train, 1502, 1.0, max_len=15, device=0)
+    oix = oracle.OracleIndex.new_from_csv(train, 1502, 1.0, 15)
+    tests = read_test_sessions(os.path.join(toy_dir, "test.txt"))
+    return gix, oix, tests
+
+
+def test_kat_should_train_and_predict(sb, oracle):
+    # mod.rs:229-310
+    items = np.array([920006, 920005, 920004, 920005, 920004, 920003, 920002], dtype=np.uint64)
+    off = np.array([0, 3, 7], dtype=np.uint64)
+    ts = np.array([1, 1], dtype=np.uint32)
+    gix = sb.VMISIndex.from_sessions(items, off, ts, 5, 5, 1.0, device=0)
+    recs = sb.predict(gix, [920005], 500, 500, 20, False)
+    assert len(recs) == 4
+    assert recs[0][0] == 920004
+    assert recs[0][1] == pytest.approx(2 * 0.9 * np.log(3.5), rel=1e-12)
+    assert [r[0] for r in recs[1:]] == [920002, 920003, 920006]
+    for r in recs[1:]:
+        assert r[1] == pytest.approx(0.9 * np.log(7.0), rel=1e-12)
+
+
+def test_readme_golden_response(sb, toy):
+    # README.md:131-155 — response of the shipped binary for item 13598 (m=1502,k=288,n=21)
+    gix, oix, _ = toy
+    recs = sb.predict(gix, [13598], 288, 1502, 21, False)
+    ids = [r[0] for r in recs]
+    assert sorted(ids) == sorted(README_13598)
+    sc = {r[0]: r[1] for r in recs}
+    # same order modulo exact-score tie classes
+    readme_scores = [sc[i] for i in README_13598]
+    assert all(readme_scores[i] >= readme_scores[i + 1] - 1e-12 for i in range(20))
+    assert ids[:3] == README_13598[:3]
+
+
+@pytest.mark.parametrize("k,m,n,L", [(50, 500, 21, 2), (288, 1502, 21, 4), (288, 1502, 21, 1), (1500, 2500, 21, 20),
+                                       (5, 10, 3, 4), (100, 100, 40, 3)])
+def test_toy_replay_matches_canonical(sb, toy, k, m, n, L):
+    gix, oix, tests = toy
+    queries, _ = evaluator_queries(tests, L)
+    assert len(queries) == 931
+    _assert_batch_equal(sb, gix, oix, queries, k, m, n)
+
+
+def test_toy_faithful_modulo_ties(sb, toy):
+    """vs the statement-by-statement restatement: same scores to 1e-12, same ids modulo tie classes
+    (k >= m here, so the unpinned k-boundary heuristic of vmis_index.rs:400-410 is not exercised)."""
+    gix, oix, tests = toy
+    queries, _ = evaluator_queries(tests, 4)
+    ids, sc, cnt = sb.predict_batch(gix, queries, 1502, 1502, 21)
+    bad = 0
+    for q, ev in enumerate(queries):
+        fi, fs = oix.predict(ev, 1502, 1502, 21, mode=0)
+        if not same_modulo_ties(ids[q, :cnt[q]], sc[q, :cnt[q]], fi, fs):
+            bad += 1
+    assert bad == 0
+
+
+@pytest.mark.parametrize("seed", range(6))
+def test_random_small_indexes(sb, oracle, seed):
+    """tiny m (eviction / truncation), duplicates, unknown items, timestamp ties, negative weights"""
+    rng = np.random.default_rng(seed)
+    n_sessions, n_items = int(rng.integers(50, 400)), int(rng.integers(8, 60))
+    items, off, ts = random_index_data(rng, n_sessions, n_items, max_len=int(rng.integers(2, 9)),
+                                       unique_ts=bool(seed % 2), id_scale=int(rng.integers(1, 1 << 20)))
+    m_build = int(rng.integers(1, 40))
+    max_len = int(rng.integers(3, 9))
+    gix = sb.VMISIndex.from_sessions(items, off, ts, m_build, max_len, 1.5, device=0)
+    oix = oracle.OracleIndex.from_sessions(items, off, ts, m_build, max_len, 1.5)
+    known = np.unique(items)
+    queries = []
+    for _ in range(300):
+        L = int(rng.integers(1, 16))
+        ev = [int(x) for x in rng.choice(known, size=L, replace=True)]
+        if rng.random() < 0.3:
+            ev[int(rng.integers(0, L))] = 999_999_999_999  # unknown item
+        queries.append(ev)
+    queries.append([999_999_999_999])
+    queries.append([])
+    for k, m, n in [(3, m_build, 5), (1, 1, 1), (500, 500, 50), (7, max(1, m_build // 2), 21), (20, 64, 33)]:
+        _assert_batch_equal(sb, gix, oix, queries, k, m, n)
+
+
+def test_find_neighbors_matches_canonical(sb, oracle):
+    rng = np.random.default_rng(11)
+    items, off, ts = random_index_data(rng, 600, 40, max_len=6, unique_ts=False)
+    gix = sb.VMISIndex.from_sessions(items, off, ts, 50, 6, 1.0, device=0)
+    oix = oracle.OracleIndex.from_sessions(items, off, ts, 50, 6, 1.0)
+    known = np.unique(items)
+    queries = [[int(x) for x in rng.choice(known, size=int(rng.integers(1, 7)))] for _ in range(200)]
+    for k, m in [(10, 50), (50, 50), (3, 7), (200, 30)]:
+        sess, sim, cnt = gix.find_neighbors_batch(queries, k, m)
+        for q, ev in enumerate(queries):
+            os_, osim = oix.find_neighbors(ev, k, m, mode=1)
+            assert cnt[q] == len(os_)
+            assert np.array_equal(sess[q, :cnt[q]], os_), (q, ev, k, m)
+            assert np.array_equal(sim[q, :cnt[q]], osim)
+
+
+def test_business_rules(sb, oracle):
+    # mod.rs:162-182
+    rng = np.random.default_rng(5)
+    items, off, ts = random_index_data(rng, 500, 30, max_len=6)
+    gix = sb.VMISIndex.from_sessions(items, off, ts, 100, 6, 1.0, device=0)
+    oix = oracle.OracleIndex.from_sessions(items, off, ts, 100, 6, 1.0)
+    known = np.unique(items)
+    flags = rng.integers(0, 8, size=len(known)).astype(np.uint8)
+    gix.set_attributes(known, flags)
+    for it, f in zip(known, flags):
+        oix.set_attributes(int(it), exists=bool(f), for_sale=bool(f & 2), adult=bool(f & 4))
+        a = gix.find_attributes(int(it))
+        assert a == oix.find_attributes(int(it))
+    queries = [[int(x) for x in rng.choice(known, size=int(rng.integers(1, 5)))] for _ in range(300)]
+    _assert_batch_equal(sb, gix, oix, queries, 50, 100, 21, biz=True)
+    _assert_batch_equal(sb, gix, oix, queries, 50, 100, 21, biz=False)
+
+
+def test_long_sessions_and_limits(sb, oracle):
+    rng = np.random.default_rng(9)
+    items, off, ts = random_index_data(rng, 800, 150, max_len=8)
+    gix = sb.VMISIndex.from_sessions(items, off, ts, 64, 8, 1.0, device=0)
+    oix = oracle.OracleIndex.from_sessions(items, off, ts, 64, 8, 1.0)
+    known = np.unique(items)
+    queries = [[int(x) for x in rng.choice(known, size=L)] for L in (100, 128, 127, 64, 33, 101, 120)]
+    _assert_batch_equal(sb, gix, oix, queries, 40, 64, 21)
+    with pytest.raises(sb.VmisError) as e:
+        sb.predict_batch(gix, [[int(known[0])] * 129], 40, 64, 21)
+    assert e.value.code == -4
+    with pytest.raises(sb.VmisError):
+        sb.predict_batch(gix, queries, 4096, 64, 21)
+
+
+def test_overflow_table_path(sb, oracle):
+    """neighbour item lists larger than the shared score table → per-CTA global table"""
+    rng = np.random.default_rng(21)
+    n_items, n_sessions = 3000, 1500
+    items, off = [], [0]
+    for s in range(n_sessions):
+        tail = rng.choice(np.arange(1, n_items), size=29, replace=False)
+        items.extend(sorted([7] + [int(x) * 3 + 11 for x in tail]))   # item 7 is in every session
+        off.append(len(items))
+    items, off = np.array(items, dtype=np.uint64), np.array(off, dtype=np.uint64)
+    ts = rng.permutation(n_sessions).astype(np.uint32)
+    gix = sb.VMISIndex.from_sessions(items, off, ts, 1502, 34, 2.0, device=0)
+    oix = oracle.OracleIndex.from_sessions(items, off, ts, 1502, 34, 2.0)
+    queries = [[7], [7, int(items[5])], [int(items[3]), 7, int(items[40])]] * 5
+    _assert_batch_equal(sb, gix, oix, queries, 600, 1502, 21)
+    _assert_batch_equal(sb, gix, oix, queries, 288, 1502, 70)
+
+
+def test_synthetic_config2_batch1024(sb, oracle):
+    """BASELINE.json config 2: synthetic 1M interactions / 50k items, batch = 1024 query sessions"""
+    items, off, ts = sb.synth_sessions(42, 50_000, 193_000)
+    gix = sb.VMISIndex.from_sessions(items, off, ts, 1502, 34, 2.0, device=0)
+    oix = oracle.OracleIndex.from_sessions(items, off, ts, 1502, 34, 2.0)
+    q_items, q_off = sb.synth_queries(43, 50_000, 1024, 4)
+    queries = [list(map(int, q_items[q_off[i]:q_off[i + 1]])) for i in range(1024)]
+    ids, sc, cnt = _assert_batch_equal(sb, gix, oix, queries, 288, 1502, 21)
+    assert (cnt == 21).mean() > 0.95
+    # faithful restatement: scores within 1e-5 (north-star tolerance) wherever the neighbour set is tie-free
+    close = 0
+    for q in range(0, 1024, 8):
+        fi, fs = oix.predict(queries[q], 288, 1502, 21, mode=0)
+        if len(fi) == cnt[q] and np.allclose(fs, sc[q, :cnt[q]], rtol=1e-5, atol=0):
+            close += 1
+    assert close >= 1   # single-item queries are all-tie at the k boundary (unpinned in the reference)
+
+
+def test_device_api_and_stats(sb, oracle):
+    torch = pytest.importorskip("torch")
+    items, off, ts = sb.synth_sessions(42, 20_000, 60_000)
+    gix = sb.VMISIndex.from_sessions(items, off, ts, 1502, 34, 2.0, device=0)
+    q_items, q_off = sb.synth_queries(43, 20_000, 4096, 4)
+    n_q, n = 4096, 21
+    dev = torch.device("cuda:0")
+    d_items = torch.from_numpy(q_items.view(np.int64)).to(dev)
+    d_off = torch.from_numpy(q_off.view(np.int32)).to(dev)
+    d_ids = torch.zeros((n_q, n), dtype=torch.int64, device=dev)
+    d_sc = torch.zeros((n_q, n), dtype=torch.float64, device=dev)
+    d_cnt = torch.zeros(n_q, dtype=torch.int32, device=dev)
+    d_st = torch.zeros((n_q, 4), dtype=torch.int32, device=dev)
+    lib = sb.load_library()
+    stream = torch.cuda.current_stream().cuda_stream
+    rc = lib.vmis_predict_batch_device(gix.handle, d_items.data_ptr(), d_off.data_ptr(), n_q, 288, 1502, n, 0,
+                                       d_ids.data_ptr(), d_sc.data_ptr(), d_cnt.data_ptr(), d_st.data_ptr(),
+                                       C.c_void_p(stream))
+    assert rc == 0, lib.vmis_last_error()
+    torch.cuda.synchronize()
+    ids, sc, cnt = sb.predict_batch(gix, (q_items, q_off), 288, 1502, n)
+    assert np.array_equal(d_cnt.cpu().numpy().view(np.uint32), cnt)
+    assert np.array_equal(d_ids.cpu().numpy().view(np.uint64), ids)
+    assert np.array_equal(d_sc.cpu().numpy(), sc)
+    st = d_st.cpu().numpy()
+    assert np.array_equal(st[:, 3].astype(np.uint32), cnt)
+    assert (st[:, 1] <= 288).all() and (st[:, 0] >= st[:, 1]).all()
+
+
+def test_concurrent_host_threads(sb, toy):
+    """many host threads on one index (actix workers over Arc<VMISIndex>, serving.rs:62-94)"""
+    import threading
+    gix, oix, tests = toy
+    queries, _ = evaluator_queries(tests, 4)
+    ref = sb.predict_batch(gix, queries, 288, 1502, 21)
+    errs = []
+
+    def work():
+        try:
+            for _ in range(5):
+                got = sb.predict_batch(gix, queries, 288, 1502, 21)
+                assert all(np.array_equal(a, b) for a, b in zip(got, ref))
+        except Exception as e:  # noqa: BLE001
+            errs.append(e)
+
+    th = [threading.Thread(target=work) for _ in range(8)]
+    [t.start() for t in th]
+    [t.join() for t in th]
+    assert not errs, errs
