@@ -346,6 +346,9 @@ vmis_predict_kernel(const IndexView ix, const PredictArgs a, const LaunchPlan pl
         a.out_sess[(size_t)q * K + rank] = ix.rank_to_orig[sid];
         a.out_sim[(size_t)q * K + rank] = (double)nm / (double)u;
       }
+      for (uint32_t i = nn + tid; i < K; i += kThreads) {            // deterministic padding
+        a.out_sess[(size_t)q * K + i] = 0; a.out_sim[(size_t)q * K + i] = 0.0;
+      }
       if (tid == 0) a.out_counts[q] = nn;
       continue;
     }
@@ -432,6 +435,9 @@ vmis_predict_kernel(const IndexView ix, const PredictArgs a, const LaunchPlan pl
       first_round = false;
       __syncthreads();
       if (emitted < 32) break;
+    }
+    for (uint32_t i = written + tid; i < N; i += kThreads) {           // deterministic padding
+      a.out_ids[(size_t)q * N + i] = 0; a.out_scores[(size_t)q * N + i] = 0.0;
     }
     if (tid == 0) {
       a.out_counts[q] = written;
