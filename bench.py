@@ -204,7 +204,8 @@ def main():
     d_sc = torch.zeros((B, n), dtype=torch.float64, device=dev)
     d_cnt = torch.zeros(B, dtype=torch.int32, device=dev)
     d_st = torch.zeros((B, 4), dtype=torch.int32, device=dev)
-    stream = torch.cuda.current_stream()
+    stream = torch.cuda.Stream(device=dev)          # kernels and timing events share this stream
+    torch.cuda.set_stream(stream)
     sptr = C.c_void_p(stream.cuda_stream)
 
     def launch(b, stats=False):

@@ -96,13 +96,14 @@ int vmis_index_stats(const vmis_index_t* index, vmis_stats_t* out);
 /* predict(index, evolving_session, k, m, how_many, enable_business_logic) — mod.rs:118-215, batched.
  * Host buffers.  out_ids/out_scores are n_q × how_many, row q holds out_counts[q] recommendations in
  * `into_sorted_vec()` order (score descending, mod.rs:339-355; ties: item id ascending).  An empty evolving
- * session yields count 0 (the reference panics, mod.rs:157).  stream: cudaStream_t or NULL. */
+ * session yields count 0 (the reference panics, mod.rs:157).  stream: cudaStream_t, or NULL for a
+ * pooled internal stream.  The call returns after the results are in the host buffers. */
 int vmis_predict_batch(const vmis_index_t* index, const uint64_t* q_items, const uint32_t* q_off, uint32_t n_q,
                        uint32_t k, uint32_t m, uint32_t how_many, int enable_business_logic,
                        uint64_t* out_ids, double* out_scores, uint32_t* out_counts, void* stream);
 
 /* Same computation with every buffer already resident on the index's device (no copies, no sync;
- * work is enqueued on `stream`).  out_stats may be NULL. */
+ * work is enqueued on `stream`; NULL = the CUDA default stream).  out_stats may be NULL. */
 int vmis_predict_batch_device(const vmis_index_t* index, const uint64_t* d_q_items, const uint32_t* d_q_off,
                               uint32_t n_q, uint32_t k, uint32_t m, uint32_t how_many, int enable_business_logic,
                               uint64_t* d_out_ids, double* d_out_scores, uint32_t* d_out_counts,

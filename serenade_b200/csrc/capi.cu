@@ -320,7 +320,7 @@ int vmis_predict_batch_device(const vmis_index_t* cix, const uint64_t* d_q_items
   std::unique_ptr<CallCtx> c;
   rc = acquire_ctx(ix, &c);
   if (rc) return rc;
-  cudaStream_t stream = stream_ ? static_cast<cudaStream_t>(stream_) : c->stream;
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);   // NULL = the CUDA default stream
   vmis::PredictArgs a{};
   a.q_items = d_q_items; a.q_off = d_q_off; a.n_q = n_q; a.k = k; a.m = m; a.how_many = how_many; a.biz = biz;
   a.out_ids = d_out_ids; a.out_scores = d_out_scores; a.out_counts = d_out_counts; a.out_stats = d_out_stats;
