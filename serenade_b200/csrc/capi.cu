@@ -36,6 +36,7 @@ struct CallCtx {
   cudaEvent_t done = nullptr;      // last use of ws / buf
   void* buf = nullptr; size_t buf_cap = 0;
   void* ws = nullptr; size_t ws_cap = 0;
+  uint32_t ws_grid = 0, ws_gtab_cap = 0;   // geometry the workspace tables were initialised for
   ~CallCtx() {
     if (buf) cudaFree(buf);
     if (ws) cudaFree(ws);
@@ -155,10 +156,15 @@ int check_common(const vmis_index* ix, uint32_t k, uint32_t m, vmis::LaunchPlan*
 
 // Enqueue one batch whose buffers are all on the device.
 int run_device(vmis_index* ix, CallCtx* c, const vmis::PredictArgs& args, const vmis::LaunchPlan& plan, cudaStream_t stream) {
+  const size_t old_cap = c->ws_cap;
   const int rc = ensure(&c->ws, &c->ws_cap, vmis::workspace_bytes(plan));
   if (rc) return rc;
   CU_TRY(cudaStreamWaitEvent(stream, c->done, 0));
   const vmis::Workspace ws = vmis::carve_workspace(c->ws, plan);
+  if (c->ws_cap != old_cap || c->ws_grid != plan.grid || c->ws_gtab_cap != plan.gtab_cap) {
+    CU_TRY(vmis::init_workspace(ws, stream));
+    c->ws_grid = plan.grid; c->ws_gtab_cap = plan.gtab_cap;
+  }
   CU_TRY(vmis::launch_predict(ix->view, args, plan, ws, stream));
   CU_TRY(cudaEventRecord(c->done, stream));
   return VMIS_OK;

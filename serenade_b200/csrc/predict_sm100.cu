@@ -129,15 +129,6 @@ __device__ __forceinline__ uint32_t lookup_item(const IndexView& ix, uint64_t it
   }
 }
 
-__device__ __forceinline__ void table_add(uint32_t* keys, int32_t* vals, uint32_t mask, uint32_t idx, int32_t v) {
-  uint32_t h = (idx * 0x9E3779B1u) >> 7 & mask;
-  for (;;) {
-    uint32_t old = atomicCAS(&keys[h], kEmpty, idx);
-    if (old == kEmpty || old == idx) { atomicAdd(&vals[h], v); return; }
-    h = (h + 1) & mask;
-  }
-}
-
 // rules of mod.rs:162-182 on packed attribute bytes
 __device__ __forceinline__ bool passes_business_rules(uint32_t cur, uint32_t reco) {
   if (!(reco & VMIS_ATTR_EXISTS)) return false;
@@ -155,10 +146,197 @@ struct SmemLayout {
   uint32_t d_pos[kMaxSessionLen];
   int scan[kWarps + 1];
   uint32_t q;                        // current query
-  uint32_t nbr_count;
   uint32_t nd;
+  uint32_t n_occ;                    // occupied score-table slots of the current query
+  uint32_t overflow;                 // shared table over its occupancy budget → redo on the global table
+  uint32_t sel_ok, sel_count;
   Elem topbuf[kWarps * 32];
 };
+
+struct QueryCtx {
+  uint32_t q, nn, nd, u, last_idx, cur_attr;
+};
+
+template <typename OccT>
+__device__ __forceinline__ void table_add(uint32_t* keys, int32_t* vals, uint32_t mask, OccT* occ, uint32_t occ_cap,
+                                          SmemLayout& S, uint32_t idx, int32_t v) {
+  uint32_t h = ((idx * 0x9E3779B1u) >> 7) & mask;
+  for (;;) {
+    const uint32_t cur = *reinterpret_cast<volatile uint32_t*>(&keys[h]);
+    if (cur == idx) break;
+    if (cur == kEmpty) {
+      if (*reinterpret_cast<volatile uint32_t*>(&S.overflow)) return;
+      const uint32_t old = atomicCAS(&keys[h], kEmpty, idx);
+      if (old == kEmpty) {                       // this thread claimed a fresh slot → record it
+        const uint32_t n = atomicAdd(&S.n_occ, 1u);
+        if (n < occ_cap) occ[n] = (OccT)h; else S.overflow = 1u;
+        break;
+      }
+      if (old == idx) break;
+    }
+    h = (h + 1) & mask;
+  }
+  atomicAdd(&vals[h], v);
+}
+
+// phase 2: 8 lanes per neighbour session.  first-match position (mod.rs:133-138) → w10 = 10·linear_score
+// (mod.rs:110-116) → A[item] += w10 · numerator for every item of the session (mod.rs:144-153)
+template <typename OccT>
+__device__ __forceinline__ void accumulate(const IndexView& ix, SmemLayout& S, const QueryCtx& c, const uint2* nbr_ref,
+                                           const int32_t* nbr_val, uint32_t* keys, int32_t* vals, uint32_t mask,
+                                           OccT* occ, uint32_t occ_cap) {
+  const int grp = threadIdx.x >> 3, gl = threadIdx.x & 7;
+  for (uint32_t base = 0; base < c.nn; base += kThreads / 8) {
+    const uint32_t i = base + grp;
+    const bool active = i < c.nn;
+    uint2 r = make_uint2(0u, 0u);
+    if (active) r = nbr_ref[i];
+    const uint32_t* items = ix.sess_items + (size_t)r.x * 4;
+    uint32_t pmin = 0xFFFFFFFFu;
+    for (uint32_t t = gl; t < r.y; t += 8) {
+      const uint32_t it = items[t];
+      for (uint32_t j = 0; j < c.nd; ++j) if (S.d_idx[j] == it) pmin = min(pmin, S.d_pos[j]);
+    }
+    pmin = min(pmin, __shfl_xor_sync(kFull, pmin, 1));
+    pmin = min(pmin, __shfl_xor_sync(kFull, pmin, 2));
+    pmin = min(pmin, __shfl_xor_sync(kFull, pmin, 4));
+    const uint32_t p = pmin + 1;                                       // 1-based position (mod.rs:140)
+    const int32_t w10 = (pmin != 0xFFFFFFFFu && p < 100) ? 10 - (int32_t)p : 0;
+    const int32_t v = active ? w10 * nbr_val[i] : 0;
+    for (uint32_t t = gl; t < r.y; t += 8) table_add<OccT>(keys, vals, mask, occ, occ_cap, S, items[t], v);
+  }
+}
+
+constexpr int kIdxBits = 13;                                 // entry index bits inside a coarse key
+constexpr uint32_t kIdxMask = (1u << kIdxBits) - 1;
+
+__device__ __forceinline__ uint32_t u32_step(uint32_t x, int lane, int j, bool up) {
+  const uint32_t o = __shfl_xor_sync(kFull, x, j);
+  return (((lane & j) == 0) == up) ? max(x, o) : min(x, o);
+}
+__device__ __forceinline__ uint32_t u32_sort_desc(uint32_t x, int lane) {
+#pragma unroll
+  for (int k = 2; k <= 32; k <<= 1) {
+#pragma unroll
+    for (int j = k >> 1; j > 0; j >>= 1) x = u32_step(x, lane, j, (lane & k) == 0);
+  }
+  return x;
+}
+__device__ __forceinline__ uint32_t u32_merge_top(uint32_t top, uint32_t cand_sorted, int lane) {
+  uint32_t x = max(top, __shfl_sync(kFull, cand_sorted, 31 - lane));
+#pragma unroll
+  for (int j = 16; j > 0; j >>= 1) x = u32_step(x, lane, j, true);
+  return x;
+}
+
+// exact candidate of one occupied slot; sentinel if filtered (current item, business rules)
+__device__ __forceinline__ Elem exact_elem(const IndexView& ix, const PredictArgs& a, const QueryCtx& c, uint32_t key,
+                                           int32_t A, double denom) {
+  Elem e; e.s = 0; e.id = kEmpty;
+  if (key == kEmpty || key == c.last_idx) return e;                    // mod.rs:157-160
+  if (a.biz && !passes_business_rules(c.cur_attr, ix.attr[key])) return e;
+  const double idf = ix.idf[key];
+  const double g = idf > 0.0 ? idf : 1.0;                              // mod.rs:145-152
+  e.s = score_bits(g * (double)A / denom); e.id = key;
+  return e;
+}
+
+// phase 3: top-n by (score desc, item asc).  Fast path: a monotone 19-bit coarse key (fp32 image of the score)
+// packed with the entry index selects 32 candidates with a u32 warp-bitonic network; if that candidate set
+// provably contains the exact top-n (no coarse tie across its boundary) they are scored exactly and sorted
+// once.  Otherwise (how_many > 31, heavy ties, global table) the exact 96-bit network scans everything.
+template <bool kGlobal, typename OccT>
+__device__ __forceinline__ uint32_t select_topn(const IndexView& ix, const PredictArgs& a, SmemLayout& S,
+                                                const QueryCtx& c, const uint32_t* keys, const int32_t* vals,
+                                                const OccT* occ, uint32_t n_occ) {
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const uint32_t N = a.how_many, q = c.q;
+  const double denom = (double)(10u * c.u);
+  if (!kGlobal && N <= 31 && n_occ <= kIdxMask) {
+    uint32_t best = 0;
+    for (uint32_t base = warp * 32; base < n_occ; base += kWarps * 32) {
+      const uint32_t e = base + lane;
+      uint32_t cand = 0;
+      if (e < n_occ) {
+        const uint32_t slot = occ[e];
+        const Elem x = exact_elem(ix, a, c, keys[slot], vals[slot], denom);
+        if (x.id != kEmpty) {
+          const uint32_t fb = __float_as_uint((float)bits_score(x.s));
+          const uint32_t mono = (fb >> 31) ? ~fb : (fb | 0x80000000u);
+          cand = (mono & ~kIdxMask) | e;
+        }
+      }
+      const uint32_t worst = __shfl_sync(kFull, best, 31);
+      if (__any_sync(kFull, cand > worst)) best = u32_merge_top(best, u32_sort_desc(cand, lane), lane);
+    }
+    uint32_t* buf = reinterpret_cast<uint32_t*>(S.topbuf);
+    buf[warp * 32 + lane] = best;
+    __syncthreads();
+    if (warp == 0) {
+      best = buf[lane];
+      for (int w = 1; w < kWarps; ++w) best = u32_merge_top(best, buf[w * 32 + lane], lane);
+      const uint32_t valid = __popc(__ballot_sync(kFull, best != 0));
+      const uint32_t take = min(valid, N);
+      bool ok = valid < 32;
+      if (!ok) ok = (__shfl_sync(kFull, best, 31) >> kIdxBits) < (__shfl_sync(kFull, best, (int)N - 1) >> kIdxBits);
+      if (ok) {
+        Elem x; x.s = 0; x.id = kEmpty;
+        if (best != 0) { const uint32_t slot = occ[best & kIdxMask]; x = exact_elem(ix, a, c, keys[slot], vals[slot], denom); }
+        x = warp_sort_desc(x, lane);
+        if ((uint32_t)lane < take) {
+          a.out_ids[(size_t)q * N + lane] = ix.item_key[x.id];
+          a.out_scores[(size_t)q * N + lane] = bits_score(x.s);
+        }
+      }
+      if (lane == 0) { S.sel_ok = ok ? 1u : 0u; S.sel_count = take; }
+    }
+    __syncthreads();
+    const uint32_t ok = S.sel_ok, cnt = S.sel_count;
+    __syncthreads();
+    if (ok) return cnt;
+  }
+  // exact path: rounds of 32 over every occupied slot
+  uint32_t written = 0;
+  Elem bound; bound.s = ~0ull; bound.id = 0;                      // exclusive upper bound of the current round
+  bool first_round = true;
+  while (written < N) {
+    Elem top; top.s = 0; top.id = kEmpty;
+    for (uint32_t base = warp * 32; base < n_occ; base += kWarps * 32) {
+      const uint32_t e = base + lane;
+      Elem x; x.s = 0; x.id = kEmpty;
+      if (e < n_occ) {
+        const uint32_t slot = occ[e];
+        x = exact_elem(ix, a, c, keys[slot], vals[slot], denom);
+        if (!first_round && !better(bound, x)) { x.s = 0; x.id = kEmpty; }
+      }
+      const Elem worst = shfl_elem(top, 31);
+      if (__any_sync(kFull, better(x, worst))) top = warp_merge_top(top, warp_sort_desc(x, lane), lane);
+    }
+    S.topbuf[warp * 32 + lane] = top;
+    __syncthreads();
+    if (warp == 0) {
+      Elem best = S.topbuf[lane];
+      for (int w = 1; w < kWarps; ++w) best = warp_merge_top(best, S.topbuf[w * 32 + lane], lane);
+      const uint32_t valid = __popc(__ballot_sync(kFull, best.id != kEmpty));
+      const uint32_t take = min(valid, N - written);
+      if ((uint32_t)lane < take) {
+        a.out_ids[(size_t)q * N + written + lane] = ix.item_key[best.id];
+        a.out_scores[(size_t)q * N + written + lane] = bits_score(best.s);
+      }
+      if (lane == 0) S.sel_count = take;
+      if (take > 0) { const Elem lastE = shfl_elem(best, (int)take - 1); if (lane == 0) S.topbuf[0] = lastE; }
+    }
+    __syncthreads();
+    const uint32_t emitted = S.sel_count;
+    if (emitted > 0) bound = S.topbuf[0];
+    written += emitted;
+    first_round = false;
+    __syncthreads();
+    if (emitted < 32) break;
+  }
+  return written;
+}
+
 
 __global__ void __launch_bounds__(kThreads, 4)
 vmis_predict_kernel(const IndexView ix, const PredictArgs a, const LaunchPlan plan, const Workspace ws) {
@@ -178,6 +356,7 @@ vmis_predict_kernel(const IndexView ix, const PredictArgs a, const LaunchPlan pl
   // phase-2/3 view of the region (aliases phase 1)
   uint32_t* stab_keys = reinterpret_cast<uint32_t*>(region);
   int32_t* stab_vals = reinterpret_cast<int32_t*>(stab_keys + plan.tab_cap);
+  uint16_t* socc = reinterpret_cast<uint16_t*>(stab_vals + plan.tab_cap);
 
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const uint32_t K = a.k, M = a.m, N = a.how_many;
@@ -353,7 +532,7 @@ vmis_predict_kernel(const IndexView ix, const PredictArgs a, const LaunchPlan pl
       continue;
     }
 
-    // ------------------------------------------------------------------ phase 2
+    // ------------------------------------------------------------------ phase 2 + 3
     int my_len = 0;
     for (uint32_t i = tid; i < nn; i += kThreads) {
       const uint2 r = ix.sess_ref[nbr_sid[i]];
@@ -361,80 +540,30 @@ vmis_predict_kernel(const IndexView ix, const PredictArgs a, const LaunchPlan pl
       my_len += (int)r.y;
     }
     const uint32_t total_items = (uint32_t)block_sum(my_len, S.scan);   // also orders phase-1 reads before table init
-    uint32_t* tkeys; int32_t* tvals; uint32_t tcap;
-    if (total_items * 2 <= plan.tab_cap) { tkeys = stab_keys; tvals = stab_vals; tcap = plan.tab_cap; }
-    else {
-      tkeys = ws.gtab_keys + (size_t)blockIdx.x * ws.gtab_cap; tvals = ws.gtab_vals + (size_t)blockIdx.x * ws.gtab_cap;
-      tcap = ws.gtab_cap;
-    }
-    const uint32_t tmask = tcap - 1;
-    for (uint32_t i = tid; i < tcap; i += kThreads) { tkeys[i] = kEmpty; tvals[i] = 0; }
+    QueryCtx c;
+    c.q = q; c.nn = nn; c.nd = nd; c.u = u; c.last_idx = last_idx; c.cur_attr = cur_attr;
+    uint32_t written;
+    // shared-memory score table first; the rare query whose neighbours hold more distinct items than its
+    // occupancy budget is redone on this CTA's global table
+    for (uint32_t i = tid; i < plan.tab_cap; i += kThreads) { stab_keys[i] = kEmpty; stab_vals[i] = 0; }
+    if (tid == 0) { S.n_occ = 0; S.overflow = 0; }
     __syncthreads();
-    for (uint32_t i = tid; i < nn; i += kThreads) {
-      const uint2 r = nbr_ref[i];
-      const uint32_t* items = ix.sess_items + (size_t)r.x * 4;
-      uint32_t pmin = 0xFFFFFFFFu;                                 // first match, most recent first (mod.rs:133-138)
-      for (uint32_t t = 0; t < r.y; ++t) {
-        const uint32_t it = items[t];
-        for (uint32_t j = 0; j < nd; ++j) if (S.d_idx[j] == it) pmin = min(pmin, S.d_pos[j]);
-      }
-      const uint32_t p = pmin + 1;                                 // 1-based position (mod.rs:140)
-      const int32_t w10 = (pmin != 0xFFFFFFFFu && p < 100) ? 10 - (int32_t)p : 0;   // linear_score ×10 (mod.rs:110-116)
-      const int32_t v = w10 * nbr_val[i];
-      for (uint32_t t = 0; t < r.y; ++t) table_add(tkeys, tvals, tmask, items[t], v);
-    }
+    accumulate<uint16_t>(ix, S, c, nbr_ref, nbr_val, stab_keys, stab_vals, plan.tab_cap - 1, socc, plan.occ_cap);
     __syncthreads();
-
-    // ------------------------------------------------------------------ phase 3
-    const double denom = (double)(10u * u);
-    uint32_t written = 0;
-    Elem bound; bound.s = ~0ull; bound.id = 0;                      // exclusive upper bound of the current round
-    bool first_round = true;
-    while (written < N) {
-      Elem top; top.s = 0; top.id = kEmpty;
-      for (uint32_t base = warp * 32; base < tcap; base += kWarps * 32) {
-        const uint32_t slot = base + lane;
-        Elem c; c.s = 0; c.id = kEmpty;
-        const uint32_t key = tkeys[slot];
-        if (key != kEmpty && key != last_idx) {
-          bool ok = true;
-          if (a.biz) ok = passes_business_rules(cur_attr, ix.attr[key]);
-          if (ok) {
-            const double idf = ix.idf[key];
-            const double g = idf > 0.0 ? idf : 1.0;                // mod.rs:145-152
-            const double score = g * (double)tvals[slot] / denom;
-            c.s = score_bits(score); c.id = key;
-            if (!first_round && !better(bound, c)) { c.s = 0; c.id = kEmpty; }
-          }
-        }
-        const Elem worst = shfl_elem(top, 31);
-        if (__any_sync(kFull, better(c, worst))) {
-          c = warp_sort_desc(c, lane);
-          top = warp_merge_top(top, c, lane);
-        }
-      }
-      S.topbuf[warp * 32 + lane] = top;
+    if (!S.overflow) {
+      written = select_topn<false, uint16_t>(ix, a, S, c, stab_keys, stab_vals, socc, S.n_occ);
+    } else {
+      uint32_t* gkeys = ws.gtab_keys + (size_t)blockIdx.x * ws.gtab_cap;
+      int32_t* gvals = ws.gtab_vals + (size_t)blockIdx.x * ws.gtab_cap;
+      uint32_t* gocc = ws.gtab_occ + (size_t)blockIdx.x * (ws.gtab_cap / 2);
       __syncthreads();
-      uint32_t emitted = 0;
-      if (warp == 0) {
-        Elem best = S.topbuf[lane];
-        for (int w = 1; w < kWarps; ++w) best = warp_merge_top(best, S.topbuf[w * 32 + lane], lane);
-        const uint32_t valid = __popc(__ballot_sync(kFull, best.id != kEmpty));
-        const uint32_t take = min(valid, N - written);
-        if ((uint32_t)lane < take) {
-          a.out_ids[(size_t)q * N + written + lane] = ix.item_key[best.id];
-          a.out_scores[(size_t)q * N + written + lane] = bits_score(best.s);
-        }
-        if (lane == 0) { S.nbr_count = take; }
-        if (take > 0) { const Elem lastE = shfl_elem(best, (int)take - 1); if (lane == 0) S.topbuf[0] = lastE; }
-      }
+      if (tid == 0) { S.n_occ = 0; S.overflow = 0; }
       __syncthreads();
-      emitted = S.nbr_count;
-      if (emitted > 0) bound = S.topbuf[0];
-      written += emitted;
-      first_round = false;
+      accumulate<uint32_t>(ix, S, c, nbr_ref, nbr_val, gkeys, gvals, ws.gtab_cap - 1, gocc, ws.gtab_cap / 2);
       __syncthreads();
-      if (emitted < 32) break;
+      const uint32_t n_occ = S.n_occ;
+      written = select_topn<true, uint32_t>(ix, a, S, c, gkeys, gvals, gocc, n_occ);
+      for (uint32_t e = tid; e < n_occ; e += kThreads) { const uint32_t slot = gocc[e]; gkeys[slot] = kEmpty; gvals[slot] = 0; }
     }
     for (uint32_t i = written + tid; i < N; i += kThreads) {           // deterministic padding
       a.out_ids[(size_t)q * N + i] = 0; a.out_scores[(size_t)q * N + i] = 0.0;
@@ -464,7 +593,8 @@ int plan_launch(const IndexView& ix, uint32_t k, uint32_t m, int sm_count, Launc
   const size_t fixed = (sizeof(SmemLayout) + 15) & ~size_t(15);
   const size_t nbr = ((size_t(k) * 8 + 15) & ~size_t(15)) + size_t(k) * 8 + 16;
   const size_t r1 = size_t(p.m_eff) * 16 + size_t(p.list_cap) * 4;
-  const size_t r2 = size_t(p.tab_cap) * 8;
+  p.occ_cap = p.tab_cap / 2 + p.tab_cap / 8;                 // 62.5 % load + kThreads in-flight claims < capacity
+  const size_t r2 = size_t(p.tab_cap) * 8 + size_t(p.occ_cap) * 2;
   const size_t total = fixed + nbr + std::max(r1, r2) + 16;
   if (total > 227 * 1024) return VMIS_ERR_LIMIT;
   p.smem_bytes = (uint32_t)total;
@@ -477,7 +607,7 @@ int plan_launch(const IndexView& ix, uint32_t k, uint32_t m, int sm_count, Launc
 }
 
 size_t workspace_bytes(const LaunchPlan& plan) {
-  return 256 + size_t(plan.grid) * plan.gtab_cap * 8;
+  return 256 + size_t(plan.grid) * plan.gtab_cap * (8 + 2);
 }
 
 Workspace carve_workspace(void* base, const LaunchPlan& plan) {
@@ -486,9 +616,17 @@ Workspace carve_workspace(void* base, const LaunchPlan& plan) {
   ws.counter = reinterpret_cast<uint32_t*>(b);
   ws.gtab_keys = reinterpret_cast<uint32_t*>(b + 256);
   ws.gtab_vals = reinterpret_cast<int32_t*>(b + 256 + size_t(plan.grid) * plan.gtab_cap * 4);
+  ws.gtab_occ = reinterpret_cast<uint32_t*>(b + 256 + size_t(plan.grid) * plan.gtab_cap * 8);
   ws.gtab_cap = plan.gtab_cap;
   ws.grid = plan.grid;
   return ws;
+}
+
+cudaError_t init_workspace(const Workspace& ws, cudaStream_t stream) {
+  const size_t n = size_t(ws.grid) * ws.gtab_cap;
+  cudaError_t e = cudaMemsetAsync(ws.gtab_keys, 0xFF, n * 4, stream);
+  if (e != cudaSuccess) return e;
+  return cudaMemsetAsync(ws.gtab_vals, 0, n * 4, stream);
 }
 
 cudaError_t launch_predict(const IndexView& ix, const PredictArgs& args, const LaunchPlan& plan, const Workspace& ws,

@@ -68,11 +68,13 @@ struct PredictArgs {
 };
 
 // Persistent-CTA workspace owned by the caller: a work counter plus one global
-// overflow score table per resident CTA.
+// overflow score table per resident CTA.  Invariant: between launches every table
+// slot is {kEmpty, 0} (init_workspace() establishes it, the kernel restores it).
 struct Workspace {
   uint32_t* counter;          // 1 × u32, zeroed by the launcher
   uint32_t* gtab_keys;        // grid × gtab_cap
   int32_t* gtab_vals;         // grid × gtab_cap
+  uint32_t* gtab_occ;         // grid × gtab_cap / 2: occupied-slot lists
   uint32_t gtab_cap;          // power of two >= 2 * k * max_len
   uint32_t grid;
 };
@@ -81,6 +83,7 @@ struct LaunchPlan {
   uint32_t grid;
   uint32_t smem_bytes;
   uint32_t tab_cap;           // shared score table slots (power of two)
+  uint32_t occ_cap;           // occupancy budget of the shared table (distinct items)
   uint32_t m_eff;             // acc buffer capacity
   uint32_t list_cap;          // posting staging capacity
   uint32_t gtab_cap;
@@ -91,6 +94,8 @@ int plan_launch(const IndexView& ix, uint32_t k, uint32_t m, int sm_count, Launc
 size_t workspace_bytes(const LaunchPlan& plan);
 // carve a raw device allocation of workspace_bytes() into a Workspace
 Workspace carve_workspace(void* base, const LaunchPlan& plan);
+// One-time initialisation of a freshly carved workspace (enqueued on `stream`).
+cudaError_t init_workspace(const Workspace& ws, cudaStream_t stream);
 // Enqueues counter reset + the predict kernel on `stream`.
 cudaError_t launch_predict(const IndexView& ix, const PredictArgs& args, const LaunchPlan& plan, const Workspace& ws,
                            cudaStream_t stream);
