@@ -91,27 +91,25 @@ __device__ __forceinline__ int warp_incl_scan(int v, int lane) {
   }
   return v;
 }
-// block-wide exclusive scan; all threads must call.  s_scan has kWarps + 1 ints.
-__device__ __forceinline__ int block_excl_scan(int v, int* s_scan, int& total) {
+// Block-wide exclusive scan with ONE barrier: warp totals go to a double-buffered scratch row and every
+// warp re-scans the kWarps totals itself.  `par` alternates the row; a row is only rewritten two calls
+// later, i.e. after another barrier, so no trailing barrier is needed.  All threads must call.
+struct ScanScratch { int row[2][kWarps]; };
+__device__ __forceinline__ int block_excl_scan(int v, ScanScratch& sc, uint32_t& par, int& total) {
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  int inc = warp_incl_scan(v, lane);
-  if (lane == 31) s_scan[warp] = inc;
+  int* row = sc.row[par & 1u];
+  par ^= 1u;
+  const int inc = warp_incl_scan(v, lane);
+  if (lane == 31) row[warp] = inc;
   __syncthreads();
-  if (warp == 0) {
-    int w = lane < kWarps ? s_scan[lane] : 0;
-    int wi = warp_incl_scan(w, lane);
-    if (lane < kWarps) s_scan[lane] = wi - w;
-    if (lane == kWarps - 1) s_scan[kWarps] = wi;
-  }
-  __syncthreads();
-  int res = s_scan[warp] + inc - v;
-  total = s_scan[kWarps];
-  __syncthreads();
-  return res;
+  const int w = lane < kWarps ? row[lane] : 0;
+  const int wi = warp_incl_scan(w, lane);
+  total = __shfl_sync(kFull, wi, kWarps - 1);
+  return __shfl_sync(kFull, wi - w, warp) + inc - v;
 }
-__device__ __forceinline__ int block_sum(int v, int* s_scan) {
+__device__ __forceinline__ int block_sum(int v, ScanScratch& sc, uint32_t& par) {
   int total;
-  block_excl_scan(v, s_scan, total);
+  block_excl_scan(v, sc, par, total);
   return total;
 }
 
@@ -144,7 +142,8 @@ struct SmemLayout {
   uint64_t q_item[kMaxSessionLen];   // evolving session reversed: [pos]
   uint32_t d_idx[kMaxSessionLen];    // distinct known items, most recent first
   uint32_t d_pos[kMaxSessionLen];
-  int scan[kWarps + 1];
+  ScanScratch scan;
+  uint32_t hist[kWarps][32];         // per-warp counts of numerators >= v (top-k threshold search)
   uint32_t q;                        // current query
   uint32_t nd;
   uint32_t n_occ;                    // occupied score-table slots of the current query
@@ -154,8 +153,16 @@ struct SmemLayout {
 };
 
 struct QueryCtx {
-  uint32_t q, nn, nd, u, last_idx, cur_attr;
+  uint32_t q, u, last_idx, cur_attr;
 };
+
+constexpr uint32_t kNumMask = 0x00FFFFFFu;   // low word of an m-sample entry: [first-match pos : 8 | numerator : 24]
+// 10 x linear_score(pos + 1) (mod.rs:110-116,140-142) times the similarity numerator
+__device__ __forceinline__ int32_t session_weight10(uint32_t low) {
+  const uint32_t p = (low >> 24) + 1;
+  const int32_t w10 = p < 100 ? 10 - (int32_t)p : 0;
+  return w10 * (int32_t)(low & kNumMask);
+}
 
 template <typename OccT>
 __device__ __forceinline__ void table_add(uint32_t* keys, int32_t* vals, uint32_t mask, OccT* occ, uint32_t occ_cap,
@@ -179,31 +186,28 @@ __device__ __forceinline__ void table_add(uint32_t* keys, int32_t* vals, uint32_
   atomicAdd(&vals[h], v);
 }
 
-// phase 2: 8 lanes per neighbour session.  first-match position (mod.rs:133-138) → w10 = 10·linear_score
-// (mod.rs:110-116) → A[item] += w10 · numerator for every item of the session (mod.rs:144-153)
+// phase 2b: A[item] += w for every item of every neighbour session (mod.rs:144-153).  The neighbours' item
+// lists are treated as one flat array of `total` entries (nbr_start = exclusive prefix of the lengths); every
+// thread takes a contiguous chunk, so the work is balanced whatever the individual session lengths are.
 template <typename OccT>
-__device__ __forceinline__ void accumulate(const IndexView& ix, SmemLayout& S, const QueryCtx& c, const uint2* nbr_ref,
-                                           const int32_t* nbr_val, uint32_t* keys, int32_t* vals, uint32_t mask,
-                                           OccT* occ, uint32_t occ_cap) {
-  const int grp = threadIdx.x >> 3, gl = threadIdx.x & 7;
-  for (uint32_t base = 0; base < c.nn; base += kThreads / 8) {
-    const uint32_t i = base + grp;
-    const bool active = i < c.nn;
-    uint2 r = make_uint2(0u, 0u);
-    if (active) r = nbr_ref[i];
-    const uint32_t* items = ix.sess_items + (size_t)r.x * 4;
-    uint32_t pmin = 0xFFFFFFFFu;
-    for (uint32_t t = gl; t < r.y; t += 8) {
-      const uint32_t it = items[t];
-      for (uint32_t j = 0; j < c.nd; ++j) if (S.d_idx[j] == it) pmin = min(pmin, S.d_pos[j]);
+__device__ __forceinline__ void accumulate(const IndexView& ix, SmemLayout& S, uint32_t nn, uint32_t total,
+                                           const uint32_t* nbr_off4, const uint32_t* nbr_start, const uint32_t* nbr_w,
+                                           uint32_t* keys, int32_t* vals, uint32_t mask, OccT* occ, uint32_t occ_cap) {
+  const uint32_t chunk = (total + kThreads - 1) / kThreads;
+  uint32_t e = min((uint32_t)threadIdx.x * chunk, total);
+  const uint32_t e1 = min(e + chunk, total);
+  if (e >= e1) return;
+  uint32_t lo = 0, hi = nn;                       // last neighbour with nbr_start <= e
+  while (hi - lo > 1) { const uint32_t mid = (lo + hi) >> 1; if (nbr_start[mid] <= e) lo = mid; else hi = mid; }
+  uint32_t i = lo, start = nbr_start[i], next = nbr_start[i + 1];
+  const uint32_t* items = ix.sess_items + (size_t)nbr_off4[i] * 4;
+  int32_t w = (int32_t)nbr_w[i];
+  for (; e < e1; ++e) {
+    while (e >= next) {
+      ++i; start = next; next = nbr_start[i + 1];
+      items = ix.sess_items + (size_t)nbr_off4[i] * 4; w = (int32_t)nbr_w[i];
     }
-    pmin = min(pmin, __shfl_xor_sync(kFull, pmin, 1));
-    pmin = min(pmin, __shfl_xor_sync(kFull, pmin, 2));
-    pmin = min(pmin, __shfl_xor_sync(kFull, pmin, 4));
-    const uint32_t p = pmin + 1;                                       // 1-based position (mod.rs:140)
-    const int32_t w10 = (pmin != 0xFFFFFFFFu && p < 100) ? 10 - (int32_t)p : 0;
-    const int32_t v = active ? w10 * nbr_val[i] : 0;
-    for (uint32_t t = gl; t < r.y; t += 8) table_add<OccT>(keys, vals, mask, occ, occ_cap, S, items[t], v);
+    table_add<OccT>(keys, vals, mask, occ, occ_cap, S, items[e - start], w);
   }
 }
 
@@ -343,11 +347,12 @@ vmis_predict_kernel(const IndexView ix, const PredictArgs a, const LaunchPlan pl
   extern __shared__ __align__(16) unsigned char smem_raw[];
   SmemLayout& S = *reinterpret_cast<SmemLayout*>(smem_raw);
   unsigned char* dyn = smem_raw + ((sizeof(SmemLayout) + 15) & ~size_t(15));
-  // neighbour arrays (k entries each)
-  uint32_t* nbr_sid = reinterpret_cast<uint32_t*>(dyn);
-  int32_t* nbr_val = reinterpret_cast<int32_t*>(nbr_sid + a.k);
-  uint2* nbr_ref = reinterpret_cast<uint2*>(dyn + ((size_t(a.k) * 8 + 15) & ~size_t(15)));
-  unsigned char* region = reinterpret_cast<unsigned char*>(nbr_ref + a.k);
+  // neighbour arrays
+  uint32_t* nbr_sid = reinterpret_cast<uint32_t*>(dyn);            // [K]   time rank of the neighbour session
+  uint32_t* nbr_low = nbr_sid + a.k;                               // [K]   pos|numerator, later the weight w
+  uint32_t* nbr_off4 = nbr_low + a.k;                              // [K]   item list offset / 4
+  uint32_t* nbr_start = nbr_off4 + a.k;                            // [K+1] exclusive prefix of the list lengths
+  unsigned char* region = reinterpret_cast<unsigned char*>(nbr_start + a.k + 1);
   region = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(region) + 15) & ~uintptr_t(15));
   // phase-1 view of the region
   uint64_t* acc0 = reinterpret_cast<uint64_t*>(region);
@@ -361,6 +366,11 @@ vmis_predict_kernel(const IndexView ix, const PredictArgs a, const LaunchPlan pl
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const uint32_t K = a.k, M = a.m, N = a.how_many;
   const bool neighbors_mode = a.out_sess != nullptr;
+  // With m <= m_build a session of the m-sample is on the (truncated) posting list of EVERY evolving item it
+  // contains, so the first-match position of mod.rs:133-138 is the position of the first list it came from.
+  // Otherwise the item lists are scanned as the reference does.
+  const bool pos_from_lists = M <= ix.m_build;
+  uint32_t par = 0;                                                // scan scratch parity (block-uniform)
 
   for (;;) {
     __syncthreads();
@@ -387,7 +397,7 @@ vmis_predict_kernel(const IndexView ix, const PredictArgs a, const LaunchPlan pl
     // compact distinct known items in position order
     {
       int flag = (my_idx != kEmpty) ? 1 : 0, total;
-      int pos = block_excl_scan(flag, S.scan, total);
+      int pos = block_excl_scan(flag, S.scan, par, total);
       if (flag) { S.d_idx[pos] = my_idx; S.d_pos[pos] = (uint32_t)tid; }
       if (tid == 0) S.nd = (uint32_t)total;
     }
@@ -405,26 +415,27 @@ vmis_predict_kernel(const IndexView ix, const PredictArgs a, const LaunchPlan pl
       const uint2 ref0 = ix.post_ref[S.d_idx[0]];
       const uint32_t n0 = min(ref0.y, M);
       const uint32_t* P0 = ix.postings + (size_t)ref0.x * 4;
-      const uint32_t c0 = L - S.d_pos[0];
+      const uint32_t low0 = (S.d_pos[0] << 24) | (L - S.d_pos[0]);
       postings_visited = n0;
       if (nd == 1) {
         // single distinct known item: S = first m postings, all similarities equal → N = first k
         nn = min(n0, K);
-        for (uint32_t i = tid; i < nn; i += kThreads) { nbr_sid[i] = P0[i]; nbr_val[i] = (int32_t)c0; }
+        for (uint32_t i = tid; i < nn; i += kThreads) { nbr_sid[i] = P0[i]; nbr_low[i] = low0; }
       } else {
         uint64_t* acc = acc0;
         uint64_t* out = acc1;
-        for (uint32_t i = tid; i < n0; i += kThreads) acc[i] = ((uint64_t)P0[i] << 32) | c0;
+        for (uint32_t i = tid; i < n0; i += kThreads) acc[i] = ((uint64_t)P0[i] << 32) | low0;
         uint32_t na = n0;
         for (uint32_t j = 1; j < nd; ++j) {
           const uint2 ref = ix.post_ref[S.d_idx[j]];
           const uint32_t nb = min(min(ref.y, M), plan.list_cap);
           const uint32_t* Pj = ix.postings + (size_t)ref.x * 4;
           const uint32_t cj = L - S.d_pos[j];
+          const uint32_t lowj = (S.d_pos[j] << 24) | cj;
           postings_visited += nb;
           for (uint32_t i = tid; i < nb; i += kThreads) listbuf[i] = Pj[i];
           __syncthreads();
-          // merge-path fold: out ← first M distinct of acc ∪ B, numerators summed
+          // merge-path fold: out ← first M distinct of acc ∪ B, numerators summed, first position kept
           const uint32_t T = na + nb;
           uint32_t out_count = 0;
           for (uint32_t base = 0; base < T && out_count < M; base += kTile) {
@@ -451,13 +462,13 @@ vmis_predict_kernel(const IndexView ix, const PredictArgs a, const LaunchPlan pl
                   vmask |= 1u << s; ++ai;
                 } else {
                   const bool dup = ai > 0 && (uint32_t)(acc[ai - 1] >> 32) == bk;
-                  if (!dup) { r[s] = ((uint64_t)bk << 32) | cj; vmask |= 1u << s; }
+                  if (!dup) { r[s] = ((uint64_t)bk << 32) | lowj; vmask |= 1u << s; }
                   ++bi;
                 }
               }
             }
             int total;
-            uint32_t p = out_count + (uint32_t)block_excl_scan(__popc(vmask), S.scan, total);
+            uint32_t p = out_count + (uint32_t)block_excl_scan(__popc(vmask), S.scan, par, total);
 #pragma unroll
             for (int s = 0; s < kVT; ++s) {
               if ((vmask >> s) & 1u) { if (p < M) out[p] = r[s]; ++p; }
@@ -473,37 +484,60 @@ vmis_predict_kernel(const IndexView ix, const PredictArgs a, const LaunchPlan pl
           nn = na;
           for (uint32_t i = tid; i < na; i += kThreads) {
             const uint64_t e = acc[i];
-            nbr_sid[i] = (uint32_t)(e >> 32); nbr_val[i] = (int32_t)(uint32_t)e;
+            nbr_sid[i] = (uint32_t)(e >> 32); nbr_low[i] = (uint32_t)e;
           }
         } else {
           // v* = max v with count(num >= v) >= K  (numerators are >= 1)
           const uint32_t E = (na + kThreads - 1) / kThreads;     // contiguous chunk per thread keeps recency order
           const uint32_t e0 = min((uint32_t)tid * E, na), e1 = min(e0 + E, na);
-          uint32_t vlo = 1, vhi = L * (L + 1) / 2;
-          while (vlo < vhi) {
-            const uint32_t v = (vlo + vhi + 1) >> 1;
+          const uint32_t vmax = L * (L + 1) / 2;
+          uint32_t vstar, tot_g;
+          if (vmax <= 31) {
+            // one pass: lane v of every warp counts numerators >= v through ballots
+            uint32_t cnt = 0;
+            for (uint32_t t = 0; t < E; ++t) {
+              const uint32_t i = e0 + t;
+              const uint32_t nm = i < e1 ? ((uint32_t)acc[i] & kNumMask) : 0u;
+              for (uint32_t v = 1; v <= vmax; ++v) {
+                const uint32_t b = __ballot_sync(kFull, nm >= v);
+                if ((uint32_t)lane == v) cnt += __popc(b);
+              }
+            }
+            S.hist[warp][lane] = cnt;
+            __syncthreads();
+            uint32_t c = 0;
+#pragma unroll
+            for (int w = 0; w < kWarps; ++w) c += S.hist[w][lane];
+            const uint32_t okm = __ballot_sync(kFull, lane >= 1 && (uint32_t)lane <= vmax && c >= K);
+            vstar = 31u - (uint32_t)__clz((int)okm);             // bit 1 is always set: count(num >= 1) = na > K
+            tot_g = vstar < 31u ? __shfl_sync(kFull, c, (int)vstar + 1) : 0u;
+            if (vstar + 1 > vmax) tot_g = 0u;
+          } else {
+            uint32_t vlo = 1, vhi = vmax;
+            while (vlo < vhi) {
+              const uint32_t v = (vlo + vhi + 1) >> 1;
+              int c = 0;
+              for (uint32_t i = e0; i < e1; ++i) c += (((uint32_t)acc[i] & kNumMask) >= v);
+              if ((uint32_t)block_sum(c, S.scan, par) >= K) vlo = v; else vhi = v - 1;
+            }
+            vstar = vlo;
             int c = 0;
-            for (uint32_t i = e0; i < e1; ++i) c += ((uint32_t)acc[i] >= v);
-            if ((uint32_t)block_sum(c, S.scan) >= K) vlo = v; else vhi = v - 1;
+            for (uint32_t i = e0; i < e1; ++i) c += (((uint32_t)acc[i] & kNumMask) > vstar);
+            tot_g = (uint32_t)block_sum(c, S.scan, par);
           }
-          const uint32_t vstar = vlo;
           int cg = 0, ce = 0;
-          for (uint32_t i = e0; i < e1; ++i) { const uint32_t nm = (uint32_t)acc[i]; cg += nm > vstar; ce += nm == vstar; }
-          int tot_g, tot_e;
-          const int pre_g = block_excl_scan(cg, S.scan, tot_g);
-          int pre_e = block_excl_scan(ce, S.scan, tot_e);
-          const uint32_t quota = K - (uint32_t)tot_g;            // ties at v*: the `quota` most recent win
-          uint32_t gpos = (uint32_t)pre_g;
+          for (uint32_t i = e0; i < e1; ++i) { const uint32_t nm = (uint32_t)acc[i] & kNumMask; cg += nm > vstar; ce += nm == vstar; }
+          int tot_packed;
+          const int pre = block_excl_scan(cg | (ce << 16), S.scan, par, tot_packed);
+          uint32_t gpos = (uint32_t)pre & 0xFFFFu, pre_e = (uint32_t)pre >> 16;
+          const uint32_t quota = K - tot_g;                      // ties at v*: the `quota` most recent win
           for (uint32_t i = e0; i < e1; ++i) {
             const uint64_t e = acc[i];
-            const uint32_t nm = (uint32_t)e;
+            const uint32_t nm = (uint32_t)e & kNumMask;
             if (nm > vstar) {
-              nbr_sid[gpos] = (uint32_t)(e >> 32); nbr_val[gpos] = (int32_t)nm; ++gpos;
+              nbr_sid[gpos] = (uint32_t)(e >> 32); nbr_low[gpos] = (uint32_t)e; ++gpos;
             } else if (nm == vstar) {
-              if ((uint32_t)pre_e < quota) {
-                const uint32_t p = (uint32_t)tot_g + (uint32_t)pre_e;
-                nbr_sid[p] = (uint32_t)(e >> 32); nbr_val[p] = (int32_t)nm;
-              }
+              if (pre_e < quota) { nbr_sid[tot_g + pre_e] = (uint32_t)(e >> 32); nbr_low[tot_g + pre_e] = (uint32_t)e; }
               ++pre_e;
             }
           }
@@ -516,10 +550,10 @@ vmis_predict_kernel(const IndexView ix, const PredictArgs a, const LaunchPlan pl
     if (neighbors_mode) {
       // find_neighbors output: canonical order (num desc, recency desc); O(nn^2) ranking, not a hot path
       for (uint32_t i = tid; i < nn; i += kThreads) {
-        const uint32_t sid = nbr_sid[i]; const int32_t nm = nbr_val[i];
+        const uint32_t sid = nbr_sid[i]; const uint32_t nm = nbr_low[i] & kNumMask;
         uint32_t rank = 0;
         for (uint32_t t = 0; t < nn; ++t) {
-          const int32_t on = nbr_val[t];
+          const uint32_t on = nbr_low[t] & kNumMask;
           rank += (on > nm) || (on == nm && nbr_sid[t] > sid);
         }
         a.out_sess[(size_t)q * K + rank] = ix.rank_to_orig[sid];
@@ -532,23 +566,42 @@ vmis_predict_kernel(const IndexView ix, const PredictArgs a, const LaunchPlan pl
       continue;
     }
 
-    // ------------------------------------------------------------------ phase 2 + 3
+    // ------------------------------------------------------------------ phase 2a: neighbour directory
+    for (uint32_t i = tid; i < plan.tab_cap; i += kThreads) { stab_keys[i] = kEmpty; stab_vals[i] = 0; }
+    if (tid == 0) { S.n_occ = 0; S.overflow = 0; }
+    const uint32_t En = (nn + kThreads - 1) / kThreads;
+    const uint32_t i0 = min((uint32_t)tid * En, nn), i1 = min(i0 + En, nn);
     int my_len = 0;
-    for (uint32_t i = tid; i < nn; i += kThreads) {
+    for (uint32_t i = i0; i < i1; ++i) {
       const uint2 r = ix.sess_ref[nbr_sid[i]];
-      nbr_ref[i] = r;
-      my_len += (int)r.y;
+      nbr_off4[i] = r.x; nbr_start[i] = r.y; my_len += (int)r.y;
+      uint32_t low = nbr_low[i];
+      if (!pos_from_lists) {                                        // reference scan (mod.rs:133-138)
+        const uint32_t* items = ix.sess_items + (size_t)r.x * 4;
+        uint32_t pmin = 0xFFu;
+        for (uint32_t t = 0; t < r.y; ++t) {
+          const uint32_t it = items[t];
+          for (uint32_t j = 0; j < nd; ++j) if (S.d_idx[j] == it) pmin = min(pmin, S.d_pos[j]);
+        }
+        low = (pmin << 24) | (low & kNumMask);
+      }
+      nbr_low[i] = (uint32_t)session_weight10(low);
     }
-    const uint32_t total_items = (uint32_t)block_sum(my_len, S.scan);   // also orders phase-1 reads before table init
+    int total_i;
+    uint32_t run = (uint32_t)block_excl_scan(my_len, S.scan, par, total_i);
+    const uint32_t total_items = (uint32_t)total_i;
+    for (uint32_t i = i0; i < i1; ++i) { const uint32_t len = nbr_start[i]; nbr_start[i] = run; run += len; }
+    if (tid == 0) nbr_start[nn] = total_items;
+    __syncthreads();
+
+    // ------------------------------------------------------------------ phase 2b + 3
     QueryCtx c;
-    c.q = q; c.nn = nn; c.nd = nd; c.u = u; c.last_idx = last_idx; c.cur_attr = cur_attr;
+    c.q = q; c.u = u; c.last_idx = last_idx; c.cur_attr = cur_attr;
     uint32_t written;
     // shared-memory score table first; the rare query whose neighbours hold more distinct items than its
     // occupancy budget is redone on this CTA's global table
-    for (uint32_t i = tid; i < plan.tab_cap; i += kThreads) { stab_keys[i] = kEmpty; stab_vals[i] = 0; }
-    if (tid == 0) { S.n_occ = 0; S.overflow = 0; }
-    __syncthreads();
-    accumulate<uint16_t>(ix, S, c, nbr_ref, nbr_val, stab_keys, stab_vals, plan.tab_cap - 1, socc, plan.occ_cap);
+    accumulate<uint16_t>(ix, S, nn, total_items, nbr_off4, nbr_start, nbr_low, stab_keys, stab_vals, plan.tab_cap - 1,
+                         socc, plan.occ_cap);
     __syncthreads();
     if (!S.overflow) {
       written = select_topn<false, uint16_t>(ix, a, S, c, stab_keys, stab_vals, socc, S.n_occ);
@@ -559,7 +612,8 @@ vmis_predict_kernel(const IndexView ix, const PredictArgs a, const LaunchPlan pl
       __syncthreads();
       if (tid == 0) { S.n_occ = 0; S.overflow = 0; }
       __syncthreads();
-      accumulate<uint32_t>(ix, S, c, nbr_ref, nbr_val, gkeys, gvals, ws.gtab_cap - 1, gocc, ws.gtab_cap / 2);
+      accumulate<uint32_t>(ix, S, nn, total_items, nbr_off4, nbr_start, nbr_low, gkeys, gvals, ws.gtab_cap - 1, gocc,
+                           ws.gtab_cap / 2);
       __syncthreads();
       const uint32_t n_occ = S.n_occ;
       written = select_topn<true, uint32_t>(ix, a, S, c, gkeys, gvals, gocc, n_occ);
@@ -591,7 +645,7 @@ int plan_launch(const IndexView& ix, uint32_t k, uint32_t m, int sm_count, Launc
   uint32_t tab = next_pow2(std::max(k, 1u) * 12u);
   p.tab_cap = std::min(std::max(tab, 1024u), 8192u);
   const size_t fixed = (sizeof(SmemLayout) + 15) & ~size_t(15);
-  const size_t nbr = ((size_t(k) * 8 + 15) & ~size_t(15)) + size_t(k) * 8 + 16;
+  const size_t nbr = (size_t(k) * 4 + 1) * 4 + 16;
   const size_t r1 = size_t(p.m_eff) * 16 + size_t(p.list_cap) * 4;
   p.occ_cap = p.tab_cap / 2 + p.tab_cap / 8;                 // 62.5 % load + kThreads in-flight claims < capacity
   const size_t r2 = size_t(p.tab_cap) * 8 + size_t(p.occ_cap) * 2;
