@@ -137,20 +137,58 @@ __device__ __forceinline__ bool passes_business_rules(uint32_t cur, uint32_t rec
   return false;
 }
 
+// ---- TMA (bulk async copy) + mbarrier helpers: posting lists are contiguous, 16-byte aligned rows in HBM,
+// so one elected thread streams a whole list into shared memory with a single cp.async.bulk while the
+// block merges the previous list.
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(unsigned long long* bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(unsigned long long* bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(unsigned long long* bar, uint32_t parity) {
+  uint32_t done;
+  do {
+    asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+                 : "=r"(done) : "r"(smem_u32(bar)), "r"(parity) : "memory");
+  } while (!done);
+}
+__device__ __forceinline__ void bulk_load(void* dst_smem, const void* src_gmem, uint32_t bytes, unsigned long long* bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                   smem_u32(dst_smem)), "l"(src_gmem), "r"(bytes), "r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void fence_async_proxy() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+
 struct SmemLayout {
   // fixed part
   uint64_t q_item[kMaxSessionLen];   // evolving session reversed: [pos]
   uint32_t d_idx[kMaxSessionLen];    // distinct known items, most recent first
   uint32_t d_pos[kMaxSessionLen];
   ScanScratch scan;
-  uint32_t hist[kWarps][32];         // per-warp counts of numerators >= v (top-k threshold search)
   uint32_t q;                        // current query
   uint32_t nd;
   uint32_t n_occ;                    // occupied score-table slots of the current query
   uint32_t overflow;                 // shared table over its occupancy budget → redo on the global table
   uint32_t sel_ok, sel_count;
-  Elem topbuf[kWarps * 32];
+  uint32_t bound[kWarps];            // per-warp lower bounds of the n-th best coarse score
+  unsigned long long bar[2];         // mbarriers of the two posting-list staging buffers (TMA bulk copies)
 };
+// Scratch that aliases the neighbour arrays (dead or not yet written when it is live): the per-warp numerator
+// histogram of phase 1b and the cross-warp candidate buffers of phase 3.
+union Scratch {
+  uint32_t hist[kWarps][32];
+  Elem top[kWarps * 32];
+  struct { uint32_t top32[kWarps * 32]; uint32_t queue[kWarps][64]; } sel;
+};
+
+// bytes of the neighbour arrays (4 x K + 1 words), never smaller than the scratch that aliases them
+__host__ __device__ constexpr size_t nbr_bytes_min() { return sizeof(Scratch); }
+__host__ __device__ inline size_t nbr_bytes(uint32_t k) {
+  size_t b = (size_t(k) * 4 + 1) * 4;
+  if (b < nbr_bytes_min()) b = nbr_bytes_min();
+  return (b + 15) & ~size_t(15);
+}
 
 struct QueryCtx {
   uint32_t q, u, last_idx, cur_attr;
@@ -202,12 +240,22 @@ __device__ __forceinline__ void accumulate(const IndexView& ix, SmemLayout& S, u
   uint32_t i = lo, start = nbr_start[i], next = nbr_start[i + 1];
   const uint32_t* items = ix.sess_items + (size_t)nbr_off4[i] * 4;
   int32_t w = (int32_t)nbr_w[i];
-  for (; e < e1; ++e) {
-    while (e >= next) {
-      ++i; start = next; next = nbr_start[i + 1];
-      items = ix.sess_items + (size_t)nbr_off4[i] * 4; w = (int32_t)nbr_w[i];
+  for (; e < e1; e += 4) {                          // 4 independent gathers in flight, then 4 inserts
+    uint32_t it[4]; int32_t ww[4];
+#pragma unroll
+    for (int b = 0; b < 4; ++b) {
+      it[b] = kEmpty; ww[b] = 0;
+      if (e + b < e1) {
+        while (e + b >= next) {
+          ++i; start = next; next = nbr_start[i + 1];
+          items = ix.sess_items + (size_t)nbr_off4[i] * 4; w = (int32_t)nbr_w[i];
+        }
+        it[b] = items[e + b - start]; ww[b] = w;
+      }
     }
-    table_add<OccT>(keys, vals, mask, occ, occ_cap, S, items[e - start], w);
+#pragma unroll
+    for (int b = 0; b < 4; ++b)
+      if (e + b < e1) table_add<OccT>(keys, vals, mask, occ, occ_cap, S, it[b], ww[b]);
   }
 }
 
@@ -250,30 +298,54 @@ __device__ __forceinline__ Elem exact_elem(const IndexView& ix, const PredictArg
 // provably contains the exact top-n (no coarse tie across its boundary) they are scored exactly and sorted
 // once.  Otherwise (how_many > 31, heavy ties, global table) the exact 96-bit network scans everything.
 template <bool kGlobal, typename OccT>
-__device__ __forceinline__ uint32_t select_topn(const IndexView& ix, const PredictArgs& a, SmemLayout& S,
+__device__ __forceinline__ uint32_t select_topn(const IndexView& ix, const PredictArgs& a, SmemLayout& S, Scratch& X,
                                                 const QueryCtx& c, const uint32_t* keys, const int32_t* vals,
                                                 const OccT* occ, uint32_t n_occ) {
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const uint32_t N = a.how_many, q = c.q;
   const double denom = (double)(10u * c.u);
   if (!kGlobal && N <= 31 && n_occ <= kIdxMask) {
-    uint32_t best = 0;
-    for (uint32_t base = warp * 32; base < n_occ; base += kWarps * 32) {
-      const uint32_t e = base + lane;
-      uint32_t cand = 0;
-      if (e < n_occ) {
-        const uint32_t slot = occ[e];
-        const Elem x = exact_elem(ix, a, c, keys[slot], vals[slot], denom);
-        if (x.id != kEmpty) {
-          const uint32_t fb = __float_as_uint((float)bits_score(x.s));
-          const uint32_t mono = (fb >> 31) ? ~fb : (fb | 0x80000000u);
-          cand = (mono & ~kIdxMask) | e;
+    // coarse key of entry e (0 = filtered / out of range)
+    auto coarse = [&](uint32_t e) -> uint32_t {
+      if (e >= n_occ) return 0u;
+      const uint32_t slot = occ[e];
+      const Elem x = exact_elem(ix, a, c, keys[slot], vals[slot], denom);
+      if (x.id == kEmpty) return 0u;
+      const uint32_t fb = __float_as_uint((float)bits_score(x.s));
+      const uint32_t mono = (fb >> 31) ? ~fb : (fb | 0x80000000u);
+      return (mono & ~kIdxMask) | e;
+    };
+    // round 0: every warp sorts its first 32 entries; its N-th best is a lower bound of the global N-th best
+    uint32_t best = u32_sort_desc(coarse(warp * 32 + lane), lane);
+    if (lane == 0) S.bound[warp] = __shfl_sync(kFull, best, (int)N - 1) >> kIdxBits;
+    else (void)__shfl_sync(kFull, best, (int)N - 1);
+    __syncthreads();
+    uint32_t bound = 0;
+#pragma unroll
+    for (int w = 0; w < kWarps; ++w) bound = max(bound, S.bound[w]);
+    // later rounds: only entries at or above the bound can matter; they are queued and merged 32 at a time
+    uint32_t* queue = X.sel.queue[warp];
+    uint32_t qn = 0;
+    for (uint32_t base = (kWarps + warp) * 32; base < n_occ; base += kWarps * 32) {
+      const uint32_t cand = coarse(base + lane);
+      const bool keep = cand != 0 && (cand >> kIdxBits) >= bound;
+      const uint32_t km = __ballot_sync(kFull, keep);
+      if (km) {
+        if (keep) queue[qn + __popc(km & ((1u << lane) - 1u))] = cand;
+        qn += __popc(km);
+        __syncwarp();
+        if (qn >= 32) {
+          best = u32_merge_top(best, u32_sort_desc(queue[lane], lane), lane);
+          const uint32_t rest = (uint32_t)lane < qn - 32 ? queue[32 + lane] : 0u;
+          __syncwarp();
+          queue[lane] = rest;
+          qn -= 32;
+          __syncwarp();
         }
       }
-      const uint32_t worst = __shfl_sync(kFull, best, 31);
-      if (__any_sync(kFull, cand > worst)) best = u32_merge_top(best, u32_sort_desc(cand, lane), lane);
     }
-    uint32_t* buf = reinterpret_cast<uint32_t*>(S.topbuf);
+    if (qn > 0) best = u32_merge_top(best, u32_sort_desc((uint32_t)lane < qn ? queue[lane] : 0u, lane), lane);
+    uint32_t* buf = X.sel.top32;
     buf[warp * 32 + lane] = best;
     __syncthreads();
     if (warp == 0) {
@@ -316,11 +388,11 @@ __device__ __forceinline__ uint32_t select_topn(const IndexView& ix, const Predi
       const Elem worst = shfl_elem(top, 31);
       if (__any_sync(kFull, better(x, worst))) top = warp_merge_top(top, warp_sort_desc(x, lane), lane);
     }
-    S.topbuf[warp * 32 + lane] = top;
+    X.top[warp * 32 + lane] = top;
     __syncthreads();
     if (warp == 0) {
-      Elem best = S.topbuf[lane];
-      for (int w = 1; w < kWarps; ++w) best = warp_merge_top(best, S.topbuf[w * 32 + lane], lane);
+      Elem best = X.top[lane];
+      for (int w = 1; w < kWarps; ++w) best = warp_merge_top(best, X.top[w * 32 + lane], lane);
       const uint32_t valid = __popc(__ballot_sync(kFull, best.id != kEmpty));
       const uint32_t take = min(valid, N - written);
       if ((uint32_t)lane < take) {
@@ -328,11 +400,11 @@ __device__ __forceinline__ uint32_t select_topn(const IndexView& ix, const Predi
         a.out_scores[(size_t)q * N + written + lane] = bits_score(best.s);
       }
       if (lane == 0) S.sel_count = take;
-      if (take > 0) { const Elem lastE = shfl_elem(best, (int)take - 1); if (lane == 0) S.topbuf[0] = lastE; }
+      if (take > 0) { const Elem lastE = shfl_elem(best, (int)take - 1); if (lane == 0) X.top[0] = lastE; }
     }
     __syncthreads();
     const uint32_t emitted = S.sel_count;
-    if (emitted > 0) bound = S.topbuf[0];
+    if (emitted > 0) bound = X.top[0];
     written += emitted;
     first_round = false;
     __syncthreads();
@@ -342,18 +414,18 @@ __device__ __forceinline__ uint32_t select_topn(const IndexView& ix, const Predi
 }
 
 
-__global__ void __launch_bounds__(kThreads, 4)
+__global__ void __launch_bounds__(kThreads, 5)
 vmis_predict_kernel(const IndexView ix, const PredictArgs a, const LaunchPlan plan, const Workspace ws) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   SmemLayout& S = *reinterpret_cast<SmemLayout*>(smem_raw);
   unsigned char* dyn = smem_raw + ((sizeof(SmemLayout) + 15) & ~size_t(15));
   // neighbour arrays
+  Scratch& X = *reinterpret_cast<Scratch*>(dyn);
   uint32_t* nbr_sid = reinterpret_cast<uint32_t*>(dyn);            // [K]   time rank of the neighbour session
   uint32_t* nbr_low = nbr_sid + a.k;                               // [K]   pos|numerator, later the weight w
   uint32_t* nbr_off4 = nbr_low + a.k;                              // [K]   item list offset / 4
   uint32_t* nbr_start = nbr_off4 + a.k;                            // [K+1] exclusive prefix of the list lengths
-  unsigned char* region = reinterpret_cast<unsigned char*>(nbr_start + a.k + 1);
-  region = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(region) + 15) & ~uintptr_t(15));
+  unsigned char* region = dyn + nbr_bytes(a.k);
   // phase-1 view of the region
   uint64_t* acc0 = reinterpret_cast<uint64_t*>(region);
   uint64_t* acc1 = acc0 + plan.m_eff;
@@ -371,6 +443,11 @@ vmis_predict_kernel(const IndexView ix, const PredictArgs a, const LaunchPlan pl
   // Otherwise the item lists are scanned as the reference does.
   const bool pos_from_lists = M <= ix.m_build;
   uint32_t par = 0;                                                // scan scratch parity (block-uniform)
+  uint32_t bar_parity = 0;                                         // bit b: phase parity of S.bar[b]
+  if (tid == 0) {
+    mbar_init(&S.bar[0], 1); mbar_init(&S.bar[1], 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
 
   for (;;) {
     __syncthreads();
@@ -424,16 +501,26 @@ vmis_predict_kernel(const IndexView ix, const PredictArgs a, const LaunchPlan pl
       } else {
         uint64_t* acc = acc0;
         uint64_t* out = acc1;
+        // TMA: lists 1 and 2 start streaming into the two staging buffers while list 0 is converted
+        auto issue = [&](uint32_t j, uint32_t b) {
+          const uint2 ref = ix.post_ref[S.d_idx[j]];
+          const uint32_t bytes = ((min(min(ref.y, M), plan.list_cap) + 3u) & ~3u) * 4u;
+          mbar_expect_tx(&S.bar[b], bytes);
+          bulk_load(listbuf + (size_t)b * plan.list_cap, ix.postings + (size_t)ref.x * 4, bytes, &S.bar[b]);
+        };
+        if (tid == 0) { fence_async_proxy(); issue(1, 0); if (nd > 2) issue(2, 1); }
         for (uint32_t i = tid; i < n0; i += kThreads) acc[i] = ((uint64_t)P0[i] << 32) | low0;
         uint32_t na = n0;
         for (uint32_t j = 1; j < nd; ++j) {
+          const uint32_t bsel = (j - 1) & 1u;
+          const uint32_t* lst = listbuf + (size_t)bsel * plan.list_cap;
           const uint2 ref = ix.post_ref[S.d_idx[j]];
           const uint32_t nb = min(min(ref.y, M), plan.list_cap);
-          const uint32_t* Pj = ix.postings + (size_t)ref.x * 4;
           const uint32_t cj = L - S.d_pos[j];
           const uint32_t lowj = (S.d_pos[j] << 24) | cj;
           postings_visited += nb;
-          for (uint32_t i = tid; i < nb; i += kThreads) listbuf[i] = Pj[i];
+          mbar_wait(&S.bar[bsel], (bar_parity >> bsel) & 1u);
+          bar_parity ^= 1u << bsel;
           __syncthreads();
           // merge-path fold: out ← first M distinct of acc ∪ B, numerators summed, first position kept
           const uint32_t T = na + nb;
@@ -444,7 +531,7 @@ vmis_predict_kernel(const IndexView ix, const PredictArgs a, const LaunchPlan pl
             uint32_t lo = d0 > nb ? d0 - nb : 0, hi = min(d0, na);
             while (lo < hi) {
               const uint32_t mid = (lo + hi) >> 1;
-              if ((uint32_t)(acc[mid] >> 32) >= listbuf[d0 - 1 - mid]) lo = mid + 1; else hi = mid;
+              if ((uint32_t)(acc[mid] >> 32) >= lst[d0 - 1 - mid]) lo = mid + 1; else hi = mid;
             }
             uint32_t ai = lo, bi = d0 - lo;
             uint64_t r[kVT];
@@ -455,7 +542,7 @@ vmis_predict_kernel(const IndexView ix, const PredictArgs a, const LaunchPlan pl
               if (d0 + s < d1) {
                 const uint64_t av = ai < na ? acc[ai] : 0ull;
                 const uint32_t ak = (uint32_t)(av >> 32);
-                const uint32_t bk = bi < nb ? listbuf[bi] : 0u;
+                const uint32_t bk = bi < nb ? lst[bi] : 0u;
                 const bool takeA = (ai < na) && (bi >= nb || ak >= bk);
                 if (takeA) {
                   r[s] = av + ((bi < nb && bk == ak) ? cj : 0u);
@@ -476,6 +563,7 @@ vmis_predict_kernel(const IndexView ix, const PredictArgs a, const LaunchPlan pl
             out_count = min(M, out_count + (uint32_t)total);
           }
           __syncthreads();
+          if (tid == 0 && j + 2 < nd) { fence_async_proxy(); issue(j + 2, bsel); }
           uint64_t* t = acc; acc = out; out = t;
           na = out_count;
         }
@@ -503,11 +591,11 @@ vmis_predict_kernel(const IndexView ix, const PredictArgs a, const LaunchPlan pl
                 if ((uint32_t)lane == v) cnt += __popc(b);
               }
             }
-            S.hist[warp][lane] = cnt;
+            X.hist[warp][lane] = cnt;
             __syncthreads();
             uint32_t c = 0;
 #pragma unroll
-            for (int w = 0; w < kWarps; ++w) c += S.hist[w][lane];
+            for (int w = 0; w < kWarps; ++w) c += X.hist[w][lane];
             const uint32_t okm = __ballot_sync(kFull, lane >= 1 && (uint32_t)lane <= vmax && c >= K);
             vstar = 31u - (uint32_t)__clz((int)okm);             // bit 1 is always set: count(num >= 1) = na > K
             tot_g = vstar < 31u ? __shfl_sync(kFull, c, (int)vstar + 1) : 0u;
@@ -604,7 +692,7 @@ vmis_predict_kernel(const IndexView ix, const PredictArgs a, const LaunchPlan pl
                          socc, plan.occ_cap);
     __syncthreads();
     if (!S.overflow) {
-      written = select_topn<false, uint16_t>(ix, a, S, c, stab_keys, stab_vals, socc, S.n_occ);
+      written = select_topn<false, uint16_t>(ix, a, S, X, c, stab_keys, stab_vals, socc, S.n_occ);
     } else {
       uint32_t* gkeys = ws.gtab_keys + (size_t)blockIdx.x * ws.gtab_cap;
       int32_t* gvals = ws.gtab_vals + (size_t)blockIdx.x * ws.gtab_cap;
@@ -616,7 +704,7 @@ vmis_predict_kernel(const IndexView ix, const PredictArgs a, const LaunchPlan pl
                            ws.gtab_cap / 2);
       __syncthreads();
       const uint32_t n_occ = S.n_occ;
-      written = select_topn<true, uint32_t>(ix, a, S, c, gkeys, gvals, gocc, n_occ);
+      written = select_topn<true, uint32_t>(ix, a, S, X, c, gkeys, gvals, gocc, n_occ);
       for (uint32_t e = tid; e < n_occ; e += kThreads) { const uint32_t slot = gocc[e]; gkeys[slot] = kEmpty; gvals[slot] = 0; }
     }
     for (uint32_t i = written + tid; i < N; i += kThreads) {           // deterministic padding
@@ -645,14 +733,14 @@ int plan_launch(const IndexView& ix, uint32_t k, uint32_t m, int sm_count, Launc
   uint32_t tab = next_pow2(std::max(k, 1u) * 12u);
   p.tab_cap = std::min(std::max(tab, 1024u), 8192u);
   const size_t fixed = (sizeof(SmemLayout) + 15) & ~size_t(15);
-  const size_t nbr = (size_t(k) * 4 + 1) * 4 + 16;
-  const size_t r1 = size_t(p.m_eff) * 16 + size_t(p.list_cap) * 4;
+  const size_t nbr = nbr_bytes(k);
+  const size_t r1 = size_t(p.m_eff) * 16 + size_t(p.list_cap) * 8;   // two m-sample buffers + two TMA staging buffers
   p.occ_cap = p.tab_cap / 2 + p.tab_cap / 8;                 // 62.5 % load + kThreads in-flight claims < capacity
   const size_t r2 = size_t(p.tab_cap) * 8 + size_t(p.occ_cap) * 2;
   const size_t total = fixed + nbr + std::max(r1, r2) + 16;
   if (total > 227 * 1024) return VMIS_ERR_LIMIT;
   p.smem_bytes = (uint32_t)total;
-  int per_sm = (int)std::min<size_t>(4, (227 * 1024) / total);
+  int per_sm = (int)std::min<size_t>(5, (227 * 1024) / (total + 1024));   // 1 KB per CTA is reserved by the driver
   if (per_sm < 1) per_sm = 1;
   p.grid = (uint32_t)(sm_count * per_sm);
   p.gtab_cap = next_pow2(std::max(2u * std::max(k, 1u) * std::max(ix.max_len, 1u), 1024u));
