@@ -224,38 +224,26 @@ __device__ __forceinline__ void table_add(uint32_t* keys, int32_t* vals, uint32_
   atomicAdd(&vals[h], v);
 }
 
-// phase 2b: A[item] += w for every item of every neighbour session (mod.rs:144-153).  The neighbours' item
-// lists are treated as one flat array of `total` entries (nbr_start = exclusive prefix of the lengths); every
-// thread takes a contiguous chunk, so the work is balanced whatever the individual session lengths are.
+// phase 2b: A[item] += w for every item of every neighbour session (mod.rs:144-153).  Item lists are 16-byte
+// aligned and padded with kEmpty, so the neighbours' lists are walked as one flat array of QUADS (uint4 =
+// 4 items): nbr_qstart is the exclusive prefix of the quad counts, consecutive threads take consecutive quads
+// (coalesced 16-byte loads) and find the owning neighbour with a branch-uniform binary search.  The most
+// recent item of the evolving session is never inserted: it is dropped from the result anyway (mod.rs:157-160)
+// and would be the hottest slot of the table.
 template <typename OccT>
-__device__ __forceinline__ void accumulate(const IndexView& ix, SmemLayout& S, uint32_t nn, uint32_t total,
-                                           const uint32_t* nbr_off4, const uint32_t* nbr_start, const uint32_t* nbr_w,
-                                           uint32_t* keys, int32_t* vals, uint32_t mask, OccT* occ, uint32_t occ_cap) {
-  const uint32_t chunk = (total + kThreads - 1) / kThreads;
-  uint32_t e = min((uint32_t)threadIdx.x * chunk, total);
-  const uint32_t e1 = min(e + chunk, total);
-  if (e >= e1) return;
-  uint32_t lo = 0, hi = nn;                       // last neighbour with nbr_start <= e
-  while (hi - lo > 1) { const uint32_t mid = (lo + hi) >> 1; if (nbr_start[mid] <= e) lo = mid; else hi = mid; }
-  uint32_t i = lo, start = nbr_start[i], next = nbr_start[i + 1];
-  const uint32_t* items = ix.sess_items + (size_t)nbr_off4[i] * 4;
-  int32_t w = (int32_t)nbr_w[i];
-  for (; e < e1; e += 4) {                          // 4 independent gathers in flight, then 4 inserts
-    uint32_t it[4]; int32_t ww[4];
-#pragma unroll
-    for (int b = 0; b < 4; ++b) {
-      it[b] = kEmpty; ww[b] = 0;
-      if (e + b < e1) {
-        while (e + b >= next) {
-          ++i; start = next; next = nbr_start[i + 1];
-          items = ix.sess_items + (size_t)nbr_off4[i] * 4; w = (int32_t)nbr_w[i];
-        }
-        it[b] = items[e + b - start]; ww[b] = w;
-      }
-    }
-#pragma unroll
-    for (int b = 0; b < 4; ++b)
-      if (e + b < e1) table_add<OccT>(keys, vals, mask, occ, occ_cap, S, it[b], ww[b]);
+__device__ __forceinline__ void accumulate(const IndexView& ix, SmemLayout& S, uint32_t nn, uint32_t total_quads,
+                                           uint32_t last_idx, const uint32_t* nbr_off4, const uint32_t* nbr_qstart,
+                                           const uint32_t* nbr_w, uint32_t* keys, int32_t* vals, uint32_t mask, OccT* occ,
+                                           uint32_t occ_cap) {
+  for (uint32_t qd = threadIdx.x; qd < total_quads; qd += kThreads) {
+    uint32_t lo = 0, hi = nn;                       // last neighbour with nbr_qstart <= qd
+    while (hi - lo > 1) { const uint32_t mid = (lo + hi) >> 1; if (nbr_qstart[mid] <= qd) lo = mid; else hi = mid; }
+    const uint4 v = __ldg(reinterpret_cast<const uint4*>(ix.sess_items) + ((size_t)nbr_off4[lo] + (qd - nbr_qstart[lo])));
+    const int32_t w = (int32_t)nbr_w[lo];
+    if (v.x != kEmpty && v.x != last_idx) table_add<OccT>(keys, vals, mask, occ, occ_cap, S, v.x, w);
+    if (v.y != kEmpty && v.y != last_idx) table_add<OccT>(keys, vals, mask, occ, occ_cap, S, v.y, w);
+    if (v.z != kEmpty && v.z != last_idx) table_add<OccT>(keys, vals, mask, occ, occ_cap, S, v.z, w);
+    if (v.w != kEmpty && v.w != last_idx) table_add<OccT>(keys, vals, mask, occ, occ_cap, S, v.w, w);
   }
 }
 
@@ -424,7 +412,7 @@ vmis_predict_kernel(const IndexView ix, const PredictArgs a, const LaunchPlan pl
   uint32_t* nbr_sid = reinterpret_cast<uint32_t*>(dyn);            // [K]   time rank of the neighbour session
   uint32_t* nbr_low = nbr_sid + a.k;                               // [K]   pos|numerator, later the weight w
   uint32_t* nbr_off4 = nbr_low + a.k;                              // [K]   item list offset / 4
-  uint32_t* nbr_start = nbr_off4 + a.k;                            // [K+1] exclusive prefix of the list lengths
+  uint32_t* nbr_start = nbr_off4 + a.k;                            // [K+1] exclusive prefix of the list lengths in quads
   unsigned char* region = dyn + nbr_bytes(a.k);
   // phase-1 view of the region
   uint64_t* acc0 = reinterpret_cast<uint64_t*>(region);
@@ -659,10 +647,11 @@ vmis_predict_kernel(const IndexView ix, const PredictArgs a, const LaunchPlan pl
     if (tid == 0) { S.n_occ = 0; S.overflow = 0; }
     const uint32_t En = (nn + kThreads - 1) / kThreads;
     const uint32_t i0 = min((uint32_t)tid * En, nn), i1 = min(i0 + En, nn);
-    int my_len = 0;
+    int my_quads = 0, my_len = 0;
     for (uint32_t i = i0; i < i1; ++i) {
       const uint2 r = ix.sess_ref[nbr_sid[i]];
-      nbr_off4[i] = r.x; nbr_start[i] = r.y; my_len += (int)r.y;
+      const uint32_t quads = (r.y + 3u) >> 2;
+      nbr_off4[i] = r.x; nbr_start[i] = quads; my_quads += (int)quads; my_len += (int)r.y;
       uint32_t low = nbr_low[i];
       if (!pos_from_lists) {                                        // reference scan (mod.rs:133-138)
         const uint32_t* items = ix.sess_items + (size_t)r.x * 4;
@@ -675,11 +664,13 @@ vmis_predict_kernel(const IndexView ix, const PredictArgs a, const LaunchPlan pl
       }
       nbr_low[i] = (uint32_t)session_weight10(low);
     }
-    int total_i;
-    uint32_t run = (uint32_t)block_excl_scan(my_len, S.scan, par, total_i);
-    const uint32_t total_items = (uint32_t)total_i;
-    for (uint32_t i = i0; i < i1; ++i) { const uint32_t len = nbr_start[i]; nbr_start[i] = run; run += len; }
-    if (tid == 0) nbr_start[nn] = total_items;
+    int total_q;
+    uint32_t run = (uint32_t)block_excl_scan(my_quads, S.scan, par, total_q);
+    const uint32_t total_quads = (uint32_t)total_q;
+    for (uint32_t i = i0; i < i1; ++i) { const uint32_t nq = nbr_start[i]; nbr_start[i] = run; run += nq; }
+    if (tid == 0) nbr_start[nn] = total_quads;
+    uint32_t total_items = 0;
+    if (a.out_stats) total_items = (uint32_t)block_sum(my_len, S.scan, par);   // bench statistics only
     __syncthreads();
 
     // ------------------------------------------------------------------ phase 2b + 3
@@ -688,8 +679,8 @@ vmis_predict_kernel(const IndexView ix, const PredictArgs a, const LaunchPlan pl
     uint32_t written;
     // shared-memory score table first; the rare query whose neighbours hold more distinct items than its
     // occupancy budget is redone on this CTA's global table
-    accumulate<uint16_t>(ix, S, nn, total_items, nbr_off4, nbr_start, nbr_low, stab_keys, stab_vals, plan.tab_cap - 1,
-                         socc, plan.occ_cap);
+    accumulate<uint16_t>(ix, S, nn, total_quads, last_idx, nbr_off4, nbr_start, nbr_low, stab_keys, stab_vals,
+                         plan.tab_cap - 1, socc, plan.occ_cap);
     __syncthreads();
     if (!S.overflow) {
       written = select_topn<false, uint16_t>(ix, a, S, X, c, stab_keys, stab_vals, socc, S.n_occ);
@@ -700,8 +691,8 @@ vmis_predict_kernel(const IndexView ix, const PredictArgs a, const LaunchPlan pl
       __syncthreads();
       if (tid == 0) { S.n_occ = 0; S.overflow = 0; }
       __syncthreads();
-      accumulate<uint32_t>(ix, S, nn, total_items, nbr_off4, nbr_start, nbr_low, gkeys, gvals, ws.gtab_cap - 1, gocc,
-                           ws.gtab_cap / 2);
+      accumulate<uint32_t>(ix, S, nn, total_quads, last_idx, nbr_off4, nbr_start, nbr_low, gkeys, gvals,
+                           ws.gtab_cap - 1, gocc, ws.gtab_cap / 2);
       __syncthreads();
       const uint32_t n_occ = S.n_occ;
       written = select_topn<true, uint32_t>(ix, a, S, X, c, gkeys, gvals, gocc, n_occ);
