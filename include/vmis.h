@@ -159,7 +159,8 @@ int vmis_synth_queries(uint64_t seed, uint64_t n_items, uint32_t n_q, uint32_t m
 
 /* ---- misc ---------------------------------------------------------------- */
 
-const char* vmis_last_error(void);
+const char* vmis_last_error(void);   /* message of the last failure on this thread */
+int vmis_last_error_code(void);      /* its VMIS_ERR_* code (constructors return NULL on failure) */
 const char* vmis_version(void);
 
 #ifdef __cplusplus

@@ -18,11 +18,13 @@
 namespace {
 
 thread_local std::string g_err;
+thread_local int g_err_code = 0;
 
 int fail(int code, const char* fmt, ...) {
   char buf[512];
   va_list ap; va_start(ap, fmt); vsnprintf(buf, sizeof buf, fmt, ap); va_end(ap);
   g_err = buf;
+  g_err_code = code;
   return code;
 }
 #define CU_TRY(expr)                                                                     \
@@ -237,6 +239,7 @@ int host_batch(const vmis_index* cix, const uint64_t* q_items, const uint32_t* q
 extern "C" {
 
 const char* vmis_last_error(void) { return g_err.c_str(); }
+int vmis_last_error_code(void) { return g_err_code; }
 const char* vmis_version(void) { return "serenade_b200 0.1 (sm_100a)"; }
 
 vmis_index_t* vmis_index_from_sessions(const uint64_t* items, const uint64_t* sess_off, const uint32_t* sess_ts,

@@ -202,48 +202,64 @@ __device__ __forceinline__ int32_t session_weight10(uint32_t low) {
   return w10 * (int32_t)(low & kNumMask);
 }
 
+// phase 2b: A[item] += w for every item of every neighbour session (mod.rs:144-153).
+//
+// Four lanes per neighbour: item lists are 16-byte aligned and kEmpty-padded, so lane c of a group loads quads
+// c, c+4, ... of its session with one 16-byte load each.  The (up to four) items a lane holds are then inserted
+// by a warp-CONVERGED probe loop: every iteration is one linear-probing step of each lane's current item, so
+// lanes never wait inside nested divergent loops; slot claims of one iteration are aggregated into a single
+// atomic on the occupancy counter.  The most recent item of the evolving session is never inserted: it is
+// dropped from the result anyway (mod.rs:157-160) and would be the hottest slot of the table.
 template <typename OccT>
-__device__ __forceinline__ void table_add(uint32_t* keys, int32_t* vals, uint32_t mask, OccT* occ, uint32_t occ_cap,
-                                          SmemLayout& S, uint32_t idx, int32_t v) {
-  uint32_t h = ((idx * 0x9E3779B1u) >> 7) & mask;
-  for (;;) {
-    const uint32_t cur = *reinterpret_cast<volatile uint32_t*>(&keys[h]);
-    if (cur == idx) break;
-    if (cur == kEmpty) {
-      if (*reinterpret_cast<volatile uint32_t*>(&S.overflow)) return;
-      const uint32_t old = atomicCAS(&keys[h], kEmpty, idx);
-      if (old == kEmpty) {                       // this thread claimed a fresh slot → record it
-        const uint32_t n = atomicAdd(&S.n_occ, 1u);
-        if (n < occ_cap) occ[n] = (OccT)h; else S.overflow = 1u;
-        break;
+__device__ __forceinline__ void accumulate(const IndexView& ix, SmemLayout& S, uint32_t nn, uint32_t last_idx,
+                                           const uint32_t* nbr_off4, const uint32_t* nbr_len, const uint32_t* nbr_w,
+                                           uint32_t* keys, int32_t* vals, uint32_t mask, OccT* occ, uint32_t occ_cap) {
+  const uint32_t lane = threadIdx.x & 31u, sub = threadIdx.x & 3u;
+  const uint32_t lt_mask = (1u << lane) - 1u;
+  const uint4* base4 = reinterpret_cast<const uint4*>(ix.sess_items);
+  volatile uint32_t* overflow = &S.overflow;
+  for (uint32_t nb0 = 0; nb0 < nn; nb0 += kThreads / 4) {
+    const uint32_t i = nb0 + (threadIdx.x >> 2);
+    uint32_t quads = 0, off4 = 0;
+    int32_t w = 0;
+    if (i < nn) { quads = (nbr_len[i] + 3u) >> 2; off4 = nbr_off4[i]; w = (int32_t)nbr_w[i]; }
+    for (uint32_t c = sub; __any_sync(kFull, c < quads); c += 4) {
+      uint4 v = make_uint4(kEmpty, kEmpty, kEmpty, kEmpty);
+      if (c < quads) v = __ldg(base4 + off4 + c);
+      uint32_t idx = v.x, p1 = v.y, p2 = v.z, p3 = v.w;
+      int left = c < quads ? 4 : 0;
+      uint32_t h = ((idx * 0x9E3779B1u) >> 7) & mask;
+      while (__any_sync(kFull, left > 0)) {
+        const bool act = left > 0 && idx != kEmpty && idx != last_idx;
+        bool hit = false, claimed = false;
+        if (act) {
+          const uint32_t cur = *reinterpret_cast<volatile uint32_t*>(&keys[h]);
+          hit = cur == idx;
+          if (!hit && cur == kEmpty) {
+            const uint32_t old = atomicCAS(&keys[h], kEmpty, idx);
+            claimed = old == kEmpty;
+            hit = claimed || old == idx;
+          }
+        }
+        const uint32_t cm = __ballot_sync(kFull, claimed);
+        if (cm) {                                    // one atomic for all slots claimed in this step
+          const int leader = __ffs((int)cm) - 1;
+          uint32_t base = 0;
+          if ((int)lane == leader) base = atomicAdd(&S.n_occ, (uint32_t)__popc(cm));
+          base = __shfl_sync(kFull, base, leader);
+          if (claimed) {
+            const uint32_t n = base + (uint32_t)__popc(cm & lt_mask);
+            if (n < occ_cap) occ[n] = (OccT)h; else *overflow = 1u;
+          }
+        }
+        if (act && hit) atomicAdd(&vals[h], w);
+        if (left > 0) {
+          if (!act || hit) { idx = p1; p1 = p2; p2 = p3; p3 = kEmpty; --left; h = ((idx * 0x9E3779B1u) >> 7) & mask; }
+          else h = (h + 1) & mask;
+        }
+        if (cm && __any_sync(kFull, *overflow != 0u)) return;   // over budget: the caller redoes the query on the global table
       }
-      if (old == idx) break;
     }
-    h = (h + 1) & mask;
-  }
-  atomicAdd(&vals[h], v);
-}
-
-// phase 2b: A[item] += w for every item of every neighbour session (mod.rs:144-153).  Item lists are 16-byte
-// aligned and padded with kEmpty, so the neighbours' lists are walked as one flat array of QUADS (uint4 =
-// 4 items): nbr_qstart is the exclusive prefix of the quad counts, consecutive threads take consecutive quads
-// (coalesced 16-byte loads) and find the owning neighbour with a branch-uniform binary search.  The most
-// recent item of the evolving session is never inserted: it is dropped from the result anyway (mod.rs:157-160)
-// and would be the hottest slot of the table.
-template <typename OccT>
-__device__ __forceinline__ void accumulate(const IndexView& ix, SmemLayout& S, uint32_t nn, uint32_t total_quads,
-                                           uint32_t last_idx, const uint32_t* nbr_off4, const uint32_t* nbr_qstart,
-                                           const uint32_t* nbr_w, uint32_t* keys, int32_t* vals, uint32_t mask, OccT* occ,
-                                           uint32_t occ_cap) {
-  for (uint32_t qd = threadIdx.x; qd < total_quads; qd += kThreads) {
-    uint32_t lo = 0, hi = nn;                       // last neighbour with nbr_qstart <= qd
-    while (hi - lo > 1) { const uint32_t mid = (lo + hi) >> 1; if (nbr_qstart[mid] <= qd) lo = mid; else hi = mid; }
-    const uint4 v = __ldg(reinterpret_cast<const uint4*>(ix.sess_items) + ((size_t)nbr_off4[lo] + (qd - nbr_qstart[lo])));
-    const int32_t w = (int32_t)nbr_w[lo];
-    if (v.x != kEmpty && v.x != last_idx) table_add<OccT>(keys, vals, mask, occ, occ_cap, S, v.x, w);
-    if (v.y != kEmpty && v.y != last_idx) table_add<OccT>(keys, vals, mask, occ, occ_cap, S, v.y, w);
-    if (v.z != kEmpty && v.z != last_idx) table_add<OccT>(keys, vals, mask, occ, occ_cap, S, v.z, w);
-    if (v.w != kEmpty && v.w != last_idx) table_add<OccT>(keys, vals, mask, occ, occ_cap, S, v.w, w);
   }
 }
 
@@ -412,7 +428,7 @@ vmis_predict_kernel(const IndexView ix, const PredictArgs a, const LaunchPlan pl
   uint32_t* nbr_sid = reinterpret_cast<uint32_t*>(dyn);            // [K]   time rank of the neighbour session
   uint32_t* nbr_low = nbr_sid + a.k;                               // [K]   pos|numerator, later the weight w
   uint32_t* nbr_off4 = nbr_low + a.k;                              // [K]   item list offset / 4
-  uint32_t* nbr_start = nbr_off4 + a.k;                            // [K+1] exclusive prefix of the list lengths in quads
+  uint32_t* nbr_len = nbr_off4 + a.k;                              // [K]   item list length
   unsigned char* region = dyn + nbr_bytes(a.k);
   // phase-1 view of the region
   uint64_t* acc0 = reinterpret_cast<uint64_t*>(region);
@@ -645,13 +661,10 @@ vmis_predict_kernel(const IndexView ix, const PredictArgs a, const LaunchPlan pl
     // ------------------------------------------------------------------ phase 2a: neighbour directory
     for (uint32_t i = tid; i < plan.tab_cap; i += kThreads) { stab_keys[i] = kEmpty; stab_vals[i] = 0; }
     if (tid == 0) { S.n_occ = 0; S.overflow = 0; }
-    const uint32_t En = (nn + kThreads - 1) / kThreads;
-    const uint32_t i0 = min((uint32_t)tid * En, nn), i1 = min(i0 + En, nn);
-    int my_quads = 0, my_len = 0;
-    for (uint32_t i = i0; i < i1; ++i) {
+    int my_len = 0;
+    for (uint32_t i = tid; i < nn; i += kThreads) {
       const uint2 r = ix.sess_ref[nbr_sid[i]];
-      const uint32_t quads = (r.y + 3u) >> 2;
-      nbr_off4[i] = r.x; nbr_start[i] = quads; my_quads += (int)quads; my_len += (int)r.y;
+      nbr_off4[i] = r.x; nbr_len[i] = r.y; my_len += (int)r.y;
       uint32_t low = nbr_low[i];
       if (!pos_from_lists) {                                        // reference scan (mod.rs:133-138)
         const uint32_t* items = ix.sess_items + (size_t)r.x * 4;
@@ -664,11 +677,6 @@ vmis_predict_kernel(const IndexView ix, const PredictArgs a, const LaunchPlan pl
       }
       nbr_low[i] = (uint32_t)session_weight10(low);
     }
-    int total_q;
-    uint32_t run = (uint32_t)block_excl_scan(my_quads, S.scan, par, total_q);
-    const uint32_t total_quads = (uint32_t)total_q;
-    for (uint32_t i = i0; i < i1; ++i) { const uint32_t nq = nbr_start[i]; nbr_start[i] = run; run += nq; }
-    if (tid == 0) nbr_start[nn] = total_quads;
     uint32_t total_items = 0;
     if (a.out_stats) total_items = (uint32_t)block_sum(my_len, S.scan, par);   // bench statistics only
     __syncthreads();
@@ -679,8 +687,8 @@ vmis_predict_kernel(const IndexView ix, const PredictArgs a, const LaunchPlan pl
     uint32_t written;
     // shared-memory score table first; the rare query whose neighbours hold more distinct items than its
     // occupancy budget is redone on this CTA's global table
-    accumulate<uint16_t>(ix, S, nn, total_quads, last_idx, nbr_off4, nbr_start, nbr_low, stab_keys, stab_vals,
-                         plan.tab_cap - 1, socc, plan.occ_cap);
+    accumulate<uint16_t>(ix, S, nn, last_idx, nbr_off4, nbr_len, nbr_low, stab_keys, stab_vals, plan.tab_cap - 1,
+                         socc, plan.occ_cap);
     __syncthreads();
     if (!S.overflow) {
       written = select_topn<false, uint16_t>(ix, a, S, X, c, stab_keys, stab_vals, socc, S.n_occ);
@@ -691,8 +699,8 @@ vmis_predict_kernel(const IndexView ix, const PredictArgs a, const LaunchPlan pl
       __syncthreads();
       if (tid == 0) { S.n_occ = 0; S.overflow = 0; }
       __syncthreads();
-      accumulate<uint32_t>(ix, S, nn, total_quads, last_idx, nbr_off4, nbr_start, nbr_low, gkeys, gvals,
-                           ws.gtab_cap - 1, gocc, ws.gtab_cap / 2);
+      accumulate<uint32_t>(ix, S, nn, last_idx, nbr_off4, nbr_len, nbr_low, gkeys, gvals, ws.gtab_cap - 1, gocc,
+                           ws.gtab_cap / 2);
       __syncthreads();
       const uint32_t n_occ = S.n_occ;
       written = select_topn<true, uint32_t>(ix, a, S, X, c, gkeys, gvals, gocc, n_occ);

@@ -65,6 +65,7 @@ def load_library():
         "vmis_synth_sessions": (i32, [u64, u64, u64, _u64p, _u64p, _u32p, _u64p]),
         "vmis_synth_queries": (i32, [u64, u64, u32, u32, _u64p, _u32p]),
         "vmis_last_error": (C.c_char_p, []),
+        "vmis_last_error_code": (i32, []),
         "vmis_version": (C.c_char_p, []),
     }
     for name, (res, args) in sig.items():
@@ -78,7 +79,8 @@ EXPORTED_SYMBOLS = ("vmis_index_from_csv", "vmis_index_from_csv_ex", "vmis_index
                     "vmis_index_set_attributes", "vmis_index_free", "vmis_index_stats", "vmis_predict_batch",
                     "vmis_predict_batch_device", "vmis_predict", "vmis_find_neighbors_batch", "vmis_items_for_session",
                     "vmis_idf", "vmis_find_attributes", "vmis_postings", "vmis_session_timestamp",
-                    "vmis_synth_sessions", "vmis_synth_queries", "vmis_last_error", "vmis_version")
+                    "vmis_synth_sessions", "vmis_synth_queries", "vmis_last_error", "vmis_last_error_code",
+                    "vmis_version")
 
 
 def _check(rc):
@@ -105,7 +107,7 @@ class VMISIndex:
 
     def __init__(self, handle):
         if not handle:
-            raise VmisError(-1, load_library().vmis_last_error().decode())
+            raise VmisError(load_library().vmis_last_error_code(), load_library().vmis_last_error().decode())
         self._h = C.c_void_p(handle)
 
     # -- constructors -------------------------------------------------------------------------------

@@ -1,0 +1,169 @@
+"""CPU tests of the product's host side: the C-ABI library loads and exports every symbol include/vmis.h
+declares, the index builders agree with the oracle, and query entry points fail loudly without a GPU."""
+import ctypes as C
+import os
+import re
+
+import numpy as np
+import pytest
+
+from util import random_index_data
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def test_header_symbols_are_exported(sb):
+    hdr = open(os.path.join(ROOT, "include", "vmis.h")).read()
+    hdr = re.sub(r"/\*.*?\*/", "", hdr, flags=re.S)
+    declared = set(re.findall(r"\b(vmis_[a-z_0-9]+)\s*\(", hdr))
+    declared -= {"vmis_index", "vmis_stats", "vmis_query_stats"}
+    assert len(declared) >= 19
+    lib = C.CDLL(os.path.join(ROOT, "serenade_b200", "libvmis_b200.so"))
+    for name in sorted(declared):
+        assert hasattr(lib, name), f"{name} declared in include/vmis.h but not exported"
+    from serenade_b200.vmis import EXPORTED_SYMBOLS
+    assert declared == set(EXPORTED_SYMBOLS)
+    assert b"sm_100a" in sb.load_library().vmis_version()
+
+
+def test_library_has_no_oracle_dependency():
+    """the product must not link or load anything under oracle/"""
+    import subprocess
+    so = os.path.join(ROOT, "serenade_b200", "libvmis_b200.so")
+    needed = subprocess.run(["readelf", "-d", so], capture_output=True, text=True).stdout
+    assert "oracle" not in needed
+    for dirpath, _, files in os.walk(os.path.join(ROOT, "serenade_b200")):
+        for f in files:
+            if f.endswith((".py", ".cu", ".cpp", ".h")):
+                txt = open(os.path.join(dirpath, f)).read()
+                assert not re.search(r'#include\s*"[^"]*oracle|^\s*(from|import)\s+oracle|libvmis_oracle|dlopen', txt,
+                                     flags=re.M), f
+
+
+def test_queries_fail_loudly_without_gpu(sb, oracle):
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("GPU present")
+    items, off, ts = random_index_data(np.random.default_rng(0), 50, 10)
+    with pytest.raises(sb.VmisError) as e:           # device build without a device
+        sb.VMISIndex.from_sessions(items, off, ts, 10, 8, 1.0, device=0)
+    assert "no CPU fallback" in str(e.value) or "CUDA" in str(e.value)
+    hix = sb.VMISIndex.from_sessions(items, off, ts, 10, 8, 1.0, device=sb.DEVICE_NONE)
+    with pytest.raises(sb.VmisError) as e:
+        sb.predict(hix, [int(items[0])], 5, 10, 5)
+    assert e.value.code == -3
+    with pytest.raises(sb.VmisError):
+        hix.find_neighbors([int(items[0])], 5, 10)
+
+
+def test_toy_host_index_matches_oracle(sb, oracle, toy_dir):
+    train = os.path.join(toy_dir, "train.txt")
+    hix = sb.VMISIndex.new_from_csv(train, 1502, 1.0, max_len=0, device=sb.DEVICE_NONE)
+    st = hix.stats()
+    assert st["max_len"] == 15                       # restated t-digest p99.5 == exact p99.5 on the toy data
+    oix = oracle.OracleIndex.new_from_csv(train, 1502, 1.0, 15)
+    assert st["n_sessions"] == oix.num_sessions == 23753
+    assert st["n_items"] == oix.num_items == 17919
+    assert st["n_pairs_kept"] == oix.kept_pairs == 77651
+    rng = np.random.default_rng(1)
+    for s in rng.integers(0, st["n_sessions"], size=300):
+        assert np.array_equal(hix.items_for_session(int(s)), oix.items_for_session(int(s)))
+        assert hix.session_timestamp(int(s)) == oix.session_ts(int(s))
+    all_items = np.unique(np.concatenate([oix.items_for_session(int(s)) for s in range(0, 23753, 7)]))
+    checked = 0
+    for it in all_items[::5]:
+        try:
+            want = oix.idf(int(it))
+        except KeyError:
+            with pytest.raises(KeyError):
+                hix.idf(int(it))
+            continue
+        assert hix.idf(int(it)) == want              # bit-exact f64
+        assert np.array_equal(hix.postings(int(it)), oix.postings(int(it)))
+        assert hix.find_attributes(int(it)) == oix.find_attributes(int(it))
+        checked += 1
+    assert checked > 500
+
+
+@pytest.mark.parametrize("seed", range(4))
+def test_random_host_index_matches_oracle(sb, oracle, seed):
+    """truncation to m, timestamp ties (higher session idx first), max_len pruning"""
+    rng = np.random.default_rng(seed)
+    items, off, ts = random_index_data(rng, 400, 25, max_len=9, unique_ts=bool(seed % 2), id_scale=1 << 33)
+    m, max_len = int(rng.integers(1, 30)), int(rng.integers(2, 9))
+    hix = sb.VMISIndex.from_sessions(items, off, ts, m, max_len, 1.7, device=sb.DEVICE_NONE)
+    oix = oracle.OracleIndex.from_sessions(items, off, ts, m, max_len, 1.7)
+    st = hix.stats()
+    assert st["n_pairs_kept"] == oix.kept_pairs and st["n_items"] == oix.num_items
+    for it in np.unique(items):
+        try:
+            want = oix.idf(int(it))
+        except KeyError:                             # item only in pruned sessions
+            with pytest.raises(KeyError):
+                hix.idf(int(it))
+            assert len(hix.postings(int(it))) == 0
+            continue
+        assert hix.idf(int(it)) == want
+        assert np.array_equal(hix.postings(int(it)), oix.postings(int(it)))
+
+
+def test_csv_reader_quirks(sb, oracle, tmp_path):
+    """read_from_file (vmis_index.rs:591-752): header skipped, stable grouping by session id, first occurrence of a
+    duplicate item, clock only moved by non-duplicate rows, items sorted, LAST ROW DROPPED (:666-667,675-686)."""
+    p = tmp_path / "t.txt"
+    p.write_text("SessionId\tItemId\tTime\n"
+                 "7\t30\t100.0\n"
+                 "3\t10\t50.4\n"
+                 "7\t20\t90.0\n"
+                 "7\t30\t500.0\n"      # duplicate item: ignored, clock not moved
+                 "3\t11\t60.6\n"
+                 "9\t1\t70.0\n"
+                 "9\t2\t80.0\n")       # last sorted row: lost
+    hix = sb.VMISIndex.new_from_csv(str(p), 10, 1.0, max_len=10, device=sb.DEVICE_NONE)
+    oix = oracle.OracleIndex.new_from_csv(str(p), 10, 1.0, 10)
+    assert hix.stats()["n_sessions"] == oix.num_sessions == 3
+    want = [([10, 11], 61), ([20, 30], 100), ([1], 70)]
+    for s, (its, t) in enumerate(want):
+        assert list(hix.items_for_session(s)) == its == list(oix.items_for_session(s))
+        assert hix.session_timestamp(s) == t == oix.session_ts(s)
+    with pytest.raises(sb.VmisError) as e:
+        sb.VMISIndex.new_from_csv(str(tmp_path / "missing.txt"), 10, 1.0, device=sb.DEVICE_NONE)
+    assert e.value.code == -2
+
+
+def test_synthetic_generator(sb):
+    items, off, ts = sb.synth_sessions(42, 5000, 20000)
+    items2, off2, ts2 = sb.synth_sessions(42, 5000, 20000)
+    assert np.array_equal(items, items2) and np.array_equal(off, off2) and np.array_equal(ts, ts2)
+    lens = np.diff(off.astype(np.int64))
+    assert lens.min() >= 1 and lens.max() <= 34 and 4.5 < lens.mean() < 6.0
+    assert len(np.unique(ts)) == len(ts)                                  # unique timestamp per session
+    for s in range(0, 20000, 97):                                          # distinct, ascending inside a session
+        seg = items[off[s]:off[s + 1]]
+        assert (np.diff(seg.astype(np.int64)) > 0).all()
+    cnt = np.sort(np.unique(items, return_counts=True)[1])[::-1]
+    assert cnt[0] > 20 * np.median(cnt)                                    # Zipf head
+    q_items, q_off = sb.synth_queries(43, 5000, 1000, 4)
+    L = np.diff(q_off.astype(np.int64))
+    assert L.min() >= 1 and L.max() <= 4 and q_off[-1] == len(q_items)
+    assert np.isin(q_items, np.unique(sb.synth_sessions(42, 5000, 200000)[0])).mean() > 0.9
+
+
+def test_argument_errors(sb):
+    items, off, ts = random_index_data(np.random.default_rng(2), 30, 8)
+    with pytest.raises(sb.VmisError):
+        sb.VMISIndex.from_sessions(items, off, ts, 0, 8, 1.0, device=sb.DEVICE_NONE)   # m = 0
+    dup = np.array([5, 5], dtype=np.uint64)
+    with pytest.raises(sb.VmisError):
+        sb.VMISIndex.from_sessions(dup, np.array([0, 2], dtype=np.uint64), np.array([1], dtype=np.uint32), 5, 8, 1.0,
+                                   device=sb.DEVICE_NONE)
+    hix = sb.VMISIndex.from_sessions(items, off, ts, 5, 8, 1.0, device=sb.DEVICE_NONE)
+    with pytest.raises(IndexError):
+        hix.items_for_session(10 ** 6)
+    with pytest.raises(KeyError):
+        hix.idf(123456789)
+    assert hix.find_attributes(123456789) is None
+    hix.set_attributes(np.array([int(items[0])], dtype=np.uint64), np.array([6], dtype=np.uint8))
+    assert hix.find_attributes(int(items[0])) == {"is_for_sale": True, "is_adult": True}
+    hix.set_attributes(np.array([int(items[0])], dtype=np.uint64), np.array([0], dtype=np.uint8))
+    assert hix.find_attributes(int(items[0])) is None
