@@ -162,9 +162,8 @@ __device__ __forceinline__ void fence_async_proxy() { asm volatile("fence.proxy.
 
 struct SmemLayout {
   // fixed part
-  uint64_t q_item[kMaxSessionLen];   // evolving session reversed: [pos]
   uint32_t d_idx[kMaxSessionLen];    // distinct known items, most recent first
-  uint32_t d_pos[kMaxSessionLen];
+  uint8_t d_pos[kMaxSessionLen];
   ScanScratch scan;
   uint32_t q;                        // current query
   uint32_t nd;
@@ -182,10 +181,10 @@ union Scratch {
   struct { uint32_t top32[kWarps * 32]; uint32_t queue[kWarps][64]; } sel;
 };
 
-// bytes of the neighbour arrays (4 x K + 1 words), never smaller than the scratch that aliases them
+// bytes of the neighbour arrays (3 x K + 1 words), never smaller than the scratch that aliases them
 __host__ __device__ constexpr size_t nbr_bytes_min() { return sizeof(Scratch); }
 __host__ __device__ inline size_t nbr_bytes(uint32_t k) {
-  size_t b = (size_t(k) * 4 + 1) * 4;
+  size_t b = (size_t(k) * 3 + 1) * 4;
   if (b < nbr_bytes_min()) b = nbr_bytes_min();
   return (b + 15) & ~size_t(15);
 }
@@ -204,60 +203,72 @@ __device__ __forceinline__ int32_t session_weight10(uint32_t low) {
 
 // phase 2b: A[item] += w for every item of every neighbour session (mod.rs:144-153).
 //
-// Four lanes per neighbour: item lists are 16-byte aligned and kEmpty-padded, so lane c of a group loads quads
-// c, c+4, ... of its session with one 16-byte load each.  The (up to four) items a lane holds are then inserted
-// by a warp-CONVERGED probe loop: every iteration is one linear-probing step of each lane's current item, so
-// lanes never wait inside nested divergent loops; slot claims of one iteration are aggregated into a single
-// atomic on the occupancy counter.  The most recent item of the evolving session is never inserted: it is
-// dropped from the result anyway (mod.rs:157-160) and would be the hottest slot of the table.
+// The neighbours' item lists are walked as ONE flat array of `total` entries, 32 consecutive entries per warp
+// round, so every lane always has exactly one item.  The entry → neighbour map costs two broadcast loads: a
+// bitmap of list starts (fbits) and, per 32-entry word, the neighbour that owns its first entry (fdir); the
+// lane's neighbour is fdir + popcount of the starts up to its bit.  Inserts run as a warp-converged linear
+// probing loop (one probe step of every unfinished lane per iteration) with the slot claims of an iteration
+// folded into one atomic on the occupancy counter; the next round's gathers are issued before the loop.
+// The most recent item of the evolving session is never inserted: it is dropped from the result anyway
+// (mod.rs:157-160) and would be the hottest slot of the table.
+struct FlatMap {
+  const uint32_t* bits;     // [words] bit b of word w: entry 32w+b starts a neighbour's list
+  const uint16_t* dir;      // [words] neighbour owning entry 32w
+  const uint32_t* start;    // [nn+1]  first flat entry of each neighbour
+  const uint32_t* off4;     // [nn]    item list offset / 4
+  const uint32_t* w;        // [nn]    weight 10*linear_score*numerator
+};
+
 template <typename OccT>
-__device__ __forceinline__ void accumulate(const IndexView& ix, SmemLayout& S, uint32_t nn, uint32_t last_idx,
-                                           const uint32_t* nbr_off4, const uint32_t* nbr_len, const uint32_t* nbr_w,
-                                           uint32_t* keys, int32_t* vals, uint32_t mask, OccT* occ, uint32_t occ_cap) {
-  const uint32_t lane = threadIdx.x & 31u, sub = threadIdx.x & 3u;
-  const uint32_t lt_mask = (1u << lane) - 1u;
-  const uint4* base4 = reinterpret_cast<const uint4*>(ix.sess_items);
+__device__ __forceinline__ void accumulate(const IndexView& ix, SmemLayout& S, const FlatMap fm, uint32_t total,
+                                           uint32_t last_idx, uint32_t* keys, int32_t* vals, uint32_t mask, OccT* occ,
+                                           uint32_t occ_cap) {
+  const uint32_t lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
+  const uint32_t lt_mask = (1u << lane) - 1u, le_mask = 0xFFFFFFFFu >> (31u - lane);
   volatile uint32_t* overflow = &S.overflow;
-  for (uint32_t nb0 = 0; nb0 < nn; nb0 += kThreads / 4) {
-    const uint32_t i = nb0 + (threadIdx.x >> 2);
-    uint32_t quads = 0, off4 = 0;
-    int32_t w = 0;
-    if (i < nn) { quads = (nbr_len[i] + 3u) >> 2; off4 = nbr_off4[i]; w = (int32_t)nbr_w[i]; }
-    for (uint32_t c = sub; __any_sync(kFull, c < quads); c += 4) {
-      uint4 v = make_uint4(kEmpty, kEmpty, kEmpty, kEmpty);
-      if (c < quads) v = __ldg(base4 + off4 + c);
-      uint32_t idx = v.x, p1 = v.y, p2 = v.z, p3 = v.w;
-      int left = c < quads ? 4 : 0;
-      uint32_t h = ((idx * 0x9E3779B1u) >> 7) & mask;
-      while (__any_sync(kFull, left > 0)) {
-        const bool act = left > 0 && idx != kEmpty && idx != last_idx;
-        bool hit = false, claimed = false;
-        if (act) {
-          const uint32_t cur = *reinterpret_cast<volatile uint32_t*>(&keys[h]);
-          hit = cur == idx;
-          if (!hit && cur == kEmpty) {
-            const uint32_t old = atomicCAS(&keys[h], kEmpty, idx);
-            claimed = old == kEmpty;
-            hit = claimed || old == idx;
-          }
+  auto gather = [&](uint32_t base, uint32_t& item, int32_t& wgt) {
+    item = kEmpty; wgt = 0;
+    const uint32_t e = base + lane;
+    if (e < total) {
+      const uint32_t word = base >> 5, b = fm.bits[word];
+      const uint32_t i = (uint32_t)fm.dir[word] + (uint32_t)__popc(b & le_mask) - (b & 1u);
+      item = __ldg(ix.sess_items + (size_t)fm.off4[i] * 4 + (e - fm.start[i]));
+      wgt = (int32_t)fm.w[i];
+      if (item == last_idx) item = kEmpty;
+    }
+  };
+  uint32_t nxt_item = kEmpty; int32_t nxt_w = 0;
+  uint32_t base = warp * 32;
+  if (base < total) gather(base, nxt_item, nxt_w);
+  for (; base < total; base += kThreads) {
+    const uint32_t idx = nxt_item;
+    const int32_t w = nxt_w;
+    if (base + kThreads < total) gather(base + kThreads, nxt_item, nxt_w);
+    bool done = idx == kEmpty;
+    uint32_t h = ((idx * 0x9E3779B1u) >> 7) & mask;
+    while (__any_sync(kFull, !done)) {
+      bool claimed = false;
+      if (!done) {
+        const uint32_t cur = *reinterpret_cast<volatile uint32_t*>(&keys[h]);
+        if (cur == idx) done = true;
+        else if (cur == kEmpty) {
+          const uint32_t old = atomicCAS(&keys[h], kEmpty, idx);
+          claimed = old == kEmpty;
+          done = claimed || old == idx;
         }
-        const uint32_t cm = __ballot_sync(kFull, claimed);
-        if (cm) {                                    // one atomic for all slots claimed in this step
-          const int leader = __ffs((int)cm) - 1;
-          uint32_t base = 0;
-          if ((int)lane == leader) base = atomicAdd(&S.n_occ, (uint32_t)__popc(cm));
-          base = __shfl_sync(kFull, base, leader);
-          if (claimed) {
-            const uint32_t n = base + (uint32_t)__popc(cm & lt_mask);
-            if (n < occ_cap) occ[n] = (OccT)h; else *overflow = 1u;
-          }
+        if (done) atomicAdd(&vals[h], w); else h = (h + 1) & mask;
+      }
+      const uint32_t cm = __ballot_sync(kFull, claimed);
+      if (cm) {                                      // one atomic for all slots claimed in this step
+        const int leader = __ffs((int)cm) - 1;
+        uint32_t nb = 0;
+        if ((int)lane == leader) nb = atomicAdd(&S.n_occ, (uint32_t)__popc(cm));
+        nb = __shfl_sync(kFull, nb, leader);
+        if (claimed) {
+          const uint32_t n = nb + (uint32_t)__popc(cm & lt_mask);
+          if (n < occ_cap) occ[n] = (OccT)h; else *overflow = 1u;
         }
-        if (act && hit) atomicAdd(&vals[h], w);
-        if (left > 0) {
-          if (!act || hit) { idx = p1; p1 = p2; p2 = p3; p3 = kEmpty; --left; h = ((idx * 0x9E3779B1u) >> 7) & mask; }
-          else h = (h + 1) & mask;
-        }
-        if (cm && __any_sync(kFull, *overflow != 0u)) return;   // over budget: the caller redoes the query on the global table
+        if (__any_sync(kFull, *overflow != 0u)) return;   // over budget: the caller redoes the query on the global table
       }
     }
   }
@@ -425,11 +436,13 @@ vmis_predict_kernel(const IndexView ix, const PredictArgs a, const LaunchPlan pl
   unsigned char* dyn = smem_raw + ((sizeof(SmemLayout) + 15) & ~size_t(15));
   // neighbour arrays
   Scratch& X = *reinterpret_cast<Scratch*>(dyn);
-  uint32_t* nbr_sid = reinterpret_cast<uint32_t*>(dyn);            // [K]   time rank of the neighbour session
-  uint32_t* nbr_low = nbr_sid + a.k;                               // [K]   pos|numerator, later the weight w
+  uint32_t* nbr_sid = reinterpret_cast<uint32_t*>(dyn);            // [K+1] time rank of the neighbour session ...
+  uint32_t* nbr_start = nbr_sid;                                   //       ... later its first flat item entry
+  uint32_t* nbr_low = nbr_sid + a.k + 1;                           // [K]   pos|numerator, later the weight w
   uint32_t* nbr_off4 = nbr_low + a.k;                              // [K]   item list offset / 4
-  uint32_t* nbr_len = nbr_off4 + a.k;                              // [K]   item list length
   unsigned char* region = dyn + nbr_bytes(a.k);
+  // phase-0 view of the region
+  uint64_t* q_item = reinterpret_cast<uint64_t*>(region);          // evolving session reversed: [pos]
   // phase-1 view of the region
   uint64_t* acc0 = reinterpret_cast<uint64_t*>(region);
   uint64_t* acc1 = acc0 + plan.m_eff;
@@ -437,7 +450,9 @@ vmis_predict_kernel(const IndexView ix, const PredictArgs a, const LaunchPlan pl
   // phase-2/3 view of the region (aliases phase 1)
   uint32_t* stab_keys = reinterpret_cast<uint32_t*>(region);
   int32_t* stab_vals = reinterpret_cast<int32_t*>(stab_keys + plan.tab_cap);
-  uint16_t* socc = reinterpret_cast<uint16_t*>(stab_vals + plan.tab_cap);
+  uint32_t* fbits = reinterpret_cast<uint32_t*>(stab_vals + plan.tab_cap);
+  uint16_t* fdir = reinterpret_cast<uint16_t*>(fbits + plan.fmap_words);
+  uint16_t* socc = fdir + plan.fmap_words;
 
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const uint32_t K = a.k, M = a.m, N = a.how_many;
@@ -464,14 +479,14 @@ vmis_predict_kernel(const IndexView ix, const PredictArgs a, const LaunchPlan pl
     const uint32_t qb = a.q_off[q];
     const uint32_t Lfull = a.q_off[q + 1] - qb;
     const uint32_t L = Lfull > (uint32_t)kMaxSessionLen ? 0u : Lfull;   // over-long sessions are rejected host-side
-    if (tid < (int)L) S.q_item[tid] = a.q_items[qb + (L - 1 - tid)];
+    if (tid < (int)L) q_item[tid] = a.q_items[qb + (L - 1 - tid)];
     __syncthreads();
     uint32_t my_idx = kEmpty;
     bool distinct = false;
     if (tid < (int)L) {
-      const uint64_t it = S.q_item[tid];
+      const uint64_t it = q_item[tid];
       distinct = true;
-      for (int t = 0; t < tid; ++t) if (S.q_item[t] == it) { distinct = false; break; }
+      for (int t = 0; t < tid; ++t) if (q_item[t] == it) { distinct = false; break; }
       if (distinct) my_idx = lookup_item(ix, it);
     }
     const uint32_t u = (uint32_t)__syncthreads_count(distinct);          // unique items incl. unknown (:335-339)
@@ -661,24 +676,36 @@ vmis_predict_kernel(const IndexView ix, const PredictArgs a, const LaunchPlan pl
     // ------------------------------------------------------------------ phase 2a: neighbour directory
     for (uint32_t i = tid; i < plan.tab_cap; i += kThreads) { stab_keys[i] = kEmpty; stab_vals[i] = 0; }
     if (tid == 0) { S.n_occ = 0; S.overflow = 0; }
+    for (uint32_t i = tid; i < plan.fmap_words; i += kThreads) fbits[i] = 0u;
+    const uint32_t En = (nn + kThreads - 1) / kThreads;             // contiguous neighbours per thread
+    const uint32_t i0 = min((uint32_t)tid * En, nn), i1 = min(i0 + En, nn);
     int my_len = 0;
-    for (uint32_t i = tid; i < nn; i += kThreads) {
+    for (uint32_t i = i0; i < i1; ++i) {
       const uint2 r = ix.sess_ref[nbr_sid[i]];
-      nbr_off4[i] = r.x; nbr_len[i] = r.y; my_len += (int)r.y;
+      nbr_off4[i] = r.x; nbr_start[i] = r.y; my_len += (int)r.y;    // length parked until the scan
       uint32_t low = nbr_low[i];
       if (!pos_from_lists) {                                        // reference scan (mod.rs:133-138)
         const uint32_t* items = ix.sess_items + (size_t)r.x * 4;
         uint32_t pmin = 0xFFu;
         for (uint32_t t = 0; t < r.y; ++t) {
           const uint32_t it = items[t];
-          for (uint32_t j = 0; j < nd; ++j) if (S.d_idx[j] == it) pmin = min(pmin, S.d_pos[j]);
+          for (uint32_t j = 0; j < nd; ++j) if (S.d_idx[j] == it) pmin = min(pmin, (uint32_t)S.d_pos[j]);
         }
         low = (pmin << 24) | (low & kNumMask);
       }
       nbr_low[i] = (uint32_t)session_weight10(low);
     }
-    uint32_t total_items = 0;
-    if (a.out_stats) total_items = (uint32_t)block_sum(my_len, S.scan, par);   // bench statistics only
+    int total_i;
+    uint32_t run = (uint32_t)block_excl_scan(my_len, S.scan, par, total_i);
+    const uint32_t total_items = (uint32_t)total_i;
+    for (uint32_t i = i0; i < i1; ++i) {
+      const uint32_t len = nbr_start[i], last = run + len - 1;
+      nbr_start[i] = run;
+      atomicOr(&fbits[run >> 5], 1u << (run & 31u));
+      for (uint32_t wd = (run + 31u) >> 5; wd <= (last >> 5); ++wd) fdir[wd] = (uint16_t)i;
+      run += len;
+    }
+    if (tid == 0) nbr_start[nn] = total_items;
     __syncthreads();
 
     // ------------------------------------------------------------------ phase 2b + 3
@@ -687,8 +714,9 @@ vmis_predict_kernel(const IndexView ix, const PredictArgs a, const LaunchPlan pl
     uint32_t written;
     // shared-memory score table first; the rare query whose neighbours hold more distinct items than its
     // occupancy budget is redone on this CTA's global table
-    accumulate<uint16_t>(ix, S, nn, last_idx, nbr_off4, nbr_len, nbr_low, stab_keys, stab_vals, plan.tab_cap - 1,
-                         socc, plan.occ_cap);
+    FlatMap fm;
+    fm.bits = fbits; fm.dir = fdir; fm.start = nbr_start; fm.off4 = nbr_off4; fm.w = nbr_low;
+    accumulate<uint16_t>(ix, S, fm, total_items, last_idx, stab_keys, stab_vals, plan.tab_cap - 1, socc, plan.occ_cap);
     __syncthreads();
     if (!S.overflow) {
       written = select_topn<false, uint16_t>(ix, a, S, X, c, stab_keys, stab_vals, socc, S.n_occ);
@@ -699,8 +727,7 @@ vmis_predict_kernel(const IndexView ix, const PredictArgs a, const LaunchPlan pl
       __syncthreads();
       if (tid == 0) { S.n_occ = 0; S.overflow = 0; }
       __syncthreads();
-      accumulate<uint32_t>(ix, S, nn, last_idx, nbr_off4, nbr_len, nbr_low, gkeys, gvals, ws.gtab_cap - 1, gocc,
-                           ws.gtab_cap / 2);
+      accumulate<uint32_t>(ix, S, fm, total_items, last_idx, gkeys, gvals, ws.gtab_cap - 1, gocc, ws.gtab_cap / 2);
       __syncthreads();
       const uint32_t n_occ = S.n_occ;
       written = select_topn<true, uint32_t>(ix, a, S, X, c, gkeys, gvals, gocc, n_occ);
@@ -735,8 +762,10 @@ int plan_launch(const IndexView& ix, uint32_t k, uint32_t m, int sm_count, Launc
   const size_t nbr = nbr_bytes(k);
   const size_t r1 = size_t(p.m_eff) * 16 + size_t(p.list_cap) * 8;   // two m-sample buffers + two TMA staging buffers
   p.occ_cap = p.tab_cap / 2 + p.tab_cap / 8;                 // 62.5 % load + kThreads in-flight claims < capacity
-  const size_t r2 = size_t(p.tab_cap) * 8 + size_t(p.occ_cap) * 2;
-  const size_t total = fixed + nbr + std::max(r1, r2) + 16;
+  p.fmap_words = (std::max(k, 1u) * std::max(ix.max_len, 1u) + 31u) / 32u + 1u;
+  if (p.fmap_words > 65535u) return VMIS_ERR_LIMIT;
+  const size_t r2 = size_t(p.tab_cap) * 8 + size_t(p.fmap_words) * 6 + size_t(p.occ_cap) * 2 + 8;
+  const size_t total = fixed + nbr + std::max(std::max(r1, r2), size_t(kMaxSessionLen) * 8) + 16;
   if (total > 227 * 1024) return VMIS_ERR_LIMIT;
   p.smem_bytes = (uint32_t)total;
   int per_sm = (int)std::min<size_t>(5, (227 * 1024) / (total + 1024));   // 1 KB per CTA is reserved by the driver

@@ -84,6 +84,7 @@ struct LaunchPlan {
   uint32_t smem_bytes;
   uint32_t tab_cap;           // shared score table slots (power of two)
   uint32_t occ_cap;           // occupancy budget of the shared table (distinct items)
+  uint32_t fmap_words;        // 32-entry words of the flat neighbour-item map (k * max_len / 32 + 1)
   uint32_t m_eff;             // acc buffer capacity
   uint32_t list_cap;          // posting staging capacity
   uint32_t gtab_cap;
