@@ -207,8 +207,8 @@ __device__ __forceinline__ int32_t session_weight10(uint32_t low) {
 // round, so every lane always has exactly one item.  The entry → neighbour map costs two broadcast loads: a
 // bitmap of list starts (fbits) and, per 32-entry word, the neighbour that owns its first entry (fdir); the
 // lane's neighbour is fdir + popcount of the starts up to its bit.  Inserts run as a warp-converged linear
-// probing loop (one probe step of every unfinished lane per iteration) with the slot claims of an iteration
-// folded into one atomic on the occupancy counter; the next round's gathers are issued before the loop.
+// probing loop (one probe step of every unfinished lane per iteration); the next round's gathers are issued
+// before the loop.  The occupied slots are compacted afterwards (compact_slots) for phase 3.
 // The most recent item of the evolving session is never inserted: it is dropped from the result anyway
 // (mod.rs:157-160) and would be the hottest slot of the table.
 struct FlatMap {
@@ -219,13 +219,12 @@ struct FlatMap {
   const uint32_t* w;        // [nn]    weight 10*linear_score*numerator
 };
 
-template <typename OccT>
+constexpr uint32_t kMaxProbe = 512;        // a probe sequence this long means the table is (nearly) full
+
 __device__ __forceinline__ void accumulate(const IndexView& ix, SmemLayout& S, const FlatMap fm, uint32_t total,
-                                           uint32_t last_idx, uint32_t* keys, int32_t* vals, uint32_t mask, OccT* occ,
-                                           uint32_t occ_cap) {
+                                           uint32_t last_idx, uint32_t* keys, int32_t* vals, uint32_t mask) {
   const uint32_t lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
-  const uint32_t lt_mask = (1u << lane) - 1u, le_mask = 0xFFFFFFFFu >> (31u - lane);
-  volatile uint32_t* overflow = &S.overflow;
+  const uint32_t le_mask = 0xFFFFFFFFu >> (31u - lane);
   auto gather = [&](uint32_t base, uint32_t& item, int32_t& wgt) {
     item = kEmpty; wgt = 0;
     const uint32_t e = base + lane;
@@ -245,30 +244,36 @@ __device__ __forceinline__ void accumulate(const IndexView& ix, SmemLayout& S, c
     const int32_t w = nxt_w;
     if (base + kThreads < total) gather(base + kThreads, nxt_item, nxt_w);
     bool done = idx == kEmpty;
-    uint32_t h = ((idx * 0x9E3779B1u) >> 7) & mask;
+    uint32_t h = ((idx * 0x9E3779B1u) >> 7) & mask, steps = 0;
     while (__any_sync(kFull, !done)) {
-      bool claimed = false;
       if (!done) {
-        const uint32_t cur = *reinterpret_cast<volatile uint32_t*>(&keys[h]);
-        if (cur == idx) done = true;
-        else if (cur == kEmpty) {
-          const uint32_t old = atomicCAS(&keys[h], kEmpty, idx);
-          claimed = old == kEmpty;
-          done = claimed || old == idx;
+        uint32_t cur = *reinterpret_cast<volatile uint32_t*>(&keys[h]);
+        if (cur == kEmpty) { cur = atomicCAS(&keys[h], kEmpty, idx); if (cur == kEmpty) cur = idx; }
+        if (cur == idx) { atomicAdd(&vals[h], w); done = true; }
+        else {
+          h = (h + 1) & mask;
+          if (++steps > kMaxProbe) { S.overflow = 1u; done = true; }
         }
-        if (done) atomicAdd(&vals[h], w); else h = (h + 1) & mask;
       }
-      const uint32_t cm = __ballot_sync(kFull, claimed);
-      if (cm) {                                      // one atomic for all slots claimed in this step
-        const int leader = __ffs((int)cm) - 1;
-        uint32_t nb = 0;
-        if ((int)lane == leader) nb = atomicAdd(&S.n_occ, (uint32_t)__popc(cm));
-        nb = __shfl_sync(kFull, nb, leader);
-        if (claimed) {
-          const uint32_t n = nb + (uint32_t)__popc(cm & lt_mask);
-          if (n < occ_cap) occ[n] = (OccT)h; else *overflow = 1u;
-        }
-        if (__any_sync(kFull, *overflow != 0u)) return;   // over budget: the caller redoes the query on the global table
+    }
+  }
+}
+
+// compaction of the occupied slots into `occ` (any order); returns through S.n_occ.  One atomic per warp round.
+template <typename OccT>
+__device__ __forceinline__ void compact_slots(SmemLayout& S, const uint32_t* keys, uint32_t cap, OccT* occ, uint32_t occ_cap) {
+  const uint32_t lane = threadIdx.x & 31u;
+  const uint32_t lt_mask = (1u << lane) - 1u;
+  for (uint32_t base = (threadIdx.x >> 5) * 32; base < cap; base += kThreads) {
+    const bool used = keys[base + lane] != kEmpty;
+    const uint32_t um = __ballot_sync(kFull, used);
+    if (um) {
+      uint32_t nb = 0;
+      if (lane == 0) nb = atomicAdd(&S.n_occ, (uint32_t)__popc(um));
+      nb = __shfl_sync(kFull, nb, 0);
+      if (used) {
+        const uint32_t n = nb + (uint32_t)__popc(um & lt_mask);
+        if (n < occ_cap) occ[n] = (OccT)(base + lane); else S.overflow = 1u;
       }
     }
   }
@@ -452,7 +457,6 @@ vmis_predict_kernel(const IndexView ix, const PredictArgs a, const LaunchPlan pl
   int32_t* stab_vals = reinterpret_cast<int32_t*>(stab_keys + plan.tab_cap);
   uint32_t* fbits = reinterpret_cast<uint32_t*>(stab_vals + plan.tab_cap);
   uint16_t* fdir = reinterpret_cast<uint16_t*>(fbits + plan.fmap_words);
-  uint16_t* socc = fdir + plan.fmap_words;
 
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const uint32_t K = a.k, M = a.m, N = a.how_many;
@@ -716,18 +720,33 @@ vmis_predict_kernel(const IndexView ix, const PredictArgs a, const LaunchPlan pl
     // occupancy budget is redone on this CTA's global table
     FlatMap fm;
     fm.bits = fbits; fm.dir = fdir; fm.start = nbr_start; fm.off4 = nbr_off4; fm.w = nbr_low;
-    accumulate<uint16_t>(ix, S, fm, total_items, last_idx, stab_keys, stab_vals, plan.tab_cap - 1, socc, plan.occ_cap);
+    accumulate(ix, S, fm, total_items, last_idx, stab_keys, stab_vals, plan.tab_cap - 1);
+    __syncthreads();
+    // the occupied-slot list reuses the flat map's storage (dead once the inserts are done)
+    uint16_t* socc = reinterpret_cast<uint16_t*>(fbits);
+    if (!S.overflow) compact_slots<uint16_t>(S, stab_keys, plan.tab_cap, socc, plan.occ_cap);
     __syncthreads();
     if (!S.overflow) {
       written = select_topn<false, uint16_t>(ix, a, S, X, c, stab_keys, stab_vals, socc, S.n_occ);
     } else {
+      // redo on this CTA's global table: big enough for every item of every neighbour, cleaned after use
       uint32_t* gkeys = ws.gtab_keys + (size_t)blockIdx.x * ws.gtab_cap;
       int32_t* gvals = ws.gtab_vals + (size_t)blockIdx.x * ws.gtab_cap;
       uint32_t* gocc = ws.gtab_occ + (size_t)blockIdx.x * (ws.gtab_cap / 2);
+      // the flat map was overwritten by the partial slot list: rebuild it
       __syncthreads();
+      for (uint32_t i = tid; i < plan.fmap_words; i += kThreads) fbits[i] = 0u;
       if (tid == 0) { S.n_occ = 0; S.overflow = 0; }
       __syncthreads();
-      accumulate<uint32_t>(ix, S, fm, total_items, last_idx, gkeys, gvals, ws.gtab_cap - 1, gocc, ws.gtab_cap / 2);
+      for (uint32_t i = tid; i < nn; i += kThreads) {
+        const uint32_t s0 = nbr_start[i], last = nbr_start[i + 1] - 1;
+        atomicOr(&fbits[s0 >> 5], 1u << (s0 & 31u));
+        for (uint32_t wd = (s0 + 31u) >> 5; wd <= (last >> 5); ++wd) fdir[wd] = (uint16_t)i;
+      }
+      __syncthreads();
+      accumulate(ix, S, fm, total_items, last_idx, gkeys, gvals, ws.gtab_cap - 1);
+      __syncthreads();
+      compact_slots<uint32_t>(S, gkeys, ws.gtab_cap, gocc, ws.gtab_cap / 2);
       __syncthreads();
       const uint32_t n_occ = S.n_occ;
       written = select_topn<true, uint32_t>(ix, a, S, X, c, gkeys, gvals, gocc, n_occ);
@@ -761,10 +780,12 @@ int plan_launch(const IndexView& ix, uint32_t k, uint32_t m, int sm_count, Launc
   const size_t fixed = (sizeof(SmemLayout) + 15) & ~size_t(15);
   const size_t nbr = nbr_bytes(k);
   const size_t r1 = size_t(p.m_eff) * 16 + size_t(p.list_cap) * 8;   // two m-sample buffers + two TMA staging buffers
-  p.occ_cap = p.tab_cap / 2 + p.tab_cap / 8;                 // 62.5 % load + kThreads in-flight claims < capacity
   p.fmap_words = (std::max(k, 1u) * std::max(ix.max_len, 1u) + 31u) / 32u + 1u;
   if (p.fmap_words > 65535u) return VMIS_ERR_LIMIT;
-  const size_t r2 = size_t(p.tab_cap) * 8 + size_t(p.fmap_words) * 6 + size_t(p.occ_cap) * 2 + 8;
+  // tail of the table region: the flat map during the inserts, the occupied-slot list (u16) afterwards
+  const size_t tail = std::max(size_t(p.fmap_words) * 6 + 4, size_t(p.tab_cap / 2 + p.tab_cap / 4) * 2);
+  p.occ_cap = (uint32_t)std::min<size_t>(tail / 2, p.tab_cap);
+  const size_t r2 = size_t(p.tab_cap) * 8 + tail + 8;
   const size_t total = fixed + nbr + std::max(std::max(r1, r2), size_t(kMaxSessionLen) * 8) + 16;
   if (total > 227 * 1024) return VMIS_ERR_LIMIT;
   p.smem_bytes = (uint32_t)total;
