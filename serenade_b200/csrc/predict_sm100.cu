@@ -244,14 +244,18 @@ __device__ __forceinline__ void accumulate(const IndexView& ix, SmemLayout& S, c
     const int32_t w = nxt_w;
     if (base + kThreads < total) gather(base + kThreads, nxt_item, nxt_w);
     bool done = idx == kEmpty;
-    uint32_t h = ((idx * 0x9E3779B1u) >> 7) & mask, steps = 0;
+    // double hashing: an odd stride visits every slot of the power-of-two table and avoids the primary
+    // clustering of linear probing (shared memory has no locality to lose)
+    const uint32_t hv = idx * 0x9E3779B1u;
+    const uint32_t stride = ((hv >> 20) | 1u) & mask;
+    uint32_t h = (hv >> 7) & mask, steps = 0;
     while (__any_sync(kFull, !done)) {
       if (!done) {
         uint32_t cur = *reinterpret_cast<volatile uint32_t*>(&keys[h]);
         if (cur == kEmpty) { cur = atomicCAS(&keys[h], kEmpty, idx); if (cur == kEmpty) cur = idx; }
         if (cur == idx) { atomicAdd(&vals[h], w); done = true; }
         else {
-          h = (h + 1) & mask;
+          h = (h + stride) & mask;
           if (++steps > kMaxProbe) { S.overflow = 1u; done = true; }
         }
       }
@@ -603,7 +607,31 @@ vmis_predict_kernel(const IndexView ix, const PredictArgs a, const LaunchPlan pl
           const uint32_t e0 = min((uint32_t)tid * E, na), e1 = min(e0 + E, na);
           const uint32_t vmax = L * (L + 1) / 2;
           uint32_t vstar, tot_g;
-          if (vmax <= 31) {
+          if (vmax <= 10 && na < 4096) {
+            // evolving sessions of <= 4 items: per-thread packed histogram (12-bit fields, counts <= m < 4096),
+            // one 64-bit shuffle reduction per half, then a 10-step suffix sum
+            unsigned long long h0 = 0, h1 = 0;                  // h0: numerators 1..5, h1: 6..10
+            for (uint32_t i = e0; i < e1; ++i) {
+              const uint32_t nm = (uint32_t)acc[i] & kNumMask;
+              if (nm <= 5) h0 += 1ull << (12 * (nm - 1)); else h1 += 1ull << (12 * (nm - 6));
+            }
+#pragma unroll
+            for (int d = 16; d > 0; d >>= 1) { h0 += __shfl_xor_sync(kFull, h0, d); h1 += __shfl_xor_sync(kFull, h1, d); }
+            unsigned long long* hw = reinterpret_cast<unsigned long long*>(X.hist);
+            if (lane == 0) { hw[warp * 2] = h0; hw[warp * 2 + 1] = h1; }
+            __syncthreads();
+            h0 = 0; h1 = 0;
+#pragma unroll
+            for (int w = 0; w < kWarps; ++w) { h0 += hw[w * 2]; h1 += hw[w * 2 + 1]; }
+            uint32_t ge = 0;                                    // count(num >= v), v descending
+            vstar = 1; tot_g = 0;
+            bool found = false;
+            for (int v = 10; v >= 1; --v) {
+              const uint32_t eq = (uint32_t)(((v <= 5 ? h0 >> (12 * (v - 1)) : h1 >> (12 * (v - 6)))) & 0xFFFull);
+              if (!found && ge + eq >= K) { vstar = (uint32_t)v; tot_g = ge; found = true; }
+              ge += eq;
+            }
+          } else if (vmax <= 31) {
             // one pass: lane v of every warp counts numerators >= v through ballots
             uint32_t cnt = 0;
             for (uint32_t t = 0; t < E; ++t) {
