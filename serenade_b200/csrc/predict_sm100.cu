@@ -263,24 +263,31 @@ __device__ __forceinline__ void accumulate(const IndexView& ix, SmemLayout& S, c
   }
 }
 
-// compaction of the occupied slots into `occ` (any order); returns through S.n_occ.  One atomic per warp round.
+// compaction of the occupied slots into `occ` (any order): every thread inspects the slots tid, tid+256, ...
+// (coalesced), one block scan places its finds.  Result count in S.n_occ; sets S.overflow if the list is too small.
 template <typename OccT>
-__device__ __forceinline__ void compact_slots(SmemLayout& S, const uint32_t* keys, uint32_t cap, OccT* occ, uint32_t occ_cap) {
-  const uint32_t lane = threadIdx.x & 31u;
-  const uint32_t lt_mask = (1u << lane) - 1u;
-  for (uint32_t base = (threadIdx.x >> 5) * 32; base < cap; base += kThreads) {
-    const bool used = keys[base + lane] != kEmpty;
-    const uint32_t um = __ballot_sync(kFull, used);
-    if (um) {
-      uint32_t nb = 0;
-      if (lane == 0) nb = atomicAdd(&S.n_occ, (uint32_t)__popc(um));
-      nb = __shfl_sync(kFull, nb, 0);
-      if (used) {
-        const uint32_t n = nb + (uint32_t)__popc(um & lt_mask);
-        if (n < occ_cap) occ[n] = (OccT)(base + lane); else S.overflow = 1u;
-      }
+__device__ __forceinline__ void compact_slots(SmemLayout& S, uint32_t& par, const uint32_t* keys, uint32_t cap, OccT* occ,
+                                              uint32_t occ_cap) {
+  const uint32_t tid = threadIdx.x;
+  uint32_t run_total = 0;
+  for (uint32_t chunk = 0; chunk < cap; chunk += kThreads * 32) {          // 32 slots per thread per pass
+    uint32_t used = 0;
+#pragma unroll 8
+    for (uint32_t j = 0; j < 32; ++j) {
+      const uint32_t slot = chunk + j * kThreads + tid;
+      if (slot < cap && keys[slot] != kEmpty) used |= 1u << j;
     }
+    int total;
+    uint32_t pos = run_total + (uint32_t)block_excl_scan(__popc(used), S.scan, par, total);
+    while (used) {
+      const uint32_t j = (uint32_t)__ffs((int)used) - 1u;
+      used &= used - 1u;
+      if (pos < occ_cap) occ[pos] = (OccT)(chunk + j * kThreads + tid);
+      ++pos;
+    }
+    run_total += (uint32_t)total;
   }
+  if (tid == 0) { S.n_occ = min(run_total, occ_cap); if (run_total > occ_cap) S.overflow = 1u; }
 }
 
 constexpr int kIdxBits = 13;                                 // entry index bits inside a coarse key
@@ -329,13 +336,19 @@ __device__ __forceinline__ uint32_t select_topn(const IndexView& ix, const Predi
   const uint32_t N = a.how_many, q = c.q;
   const double denom = (double)(10u * c.u);
   if (!kGlobal && N <= 31 && n_occ <= kIdxMask) {
-    // coarse key of entry e (0 = filtered / out of range)
+    // coarse key of entry e (0 = filtered / out of range): 19-bit monotone image of an fp32 APPROXIMATION of the
+    // score (relative error < 2^-21, far below the 2^-10 coarse unit), so exact order can only disagree with
+    // coarse order by one unit: every exact top-n element has coarse >= (n-th largest coarse) - 1.
+    const float rdenom = 1.0f / (float)denom;
     auto coarse = [&](uint32_t e) -> uint32_t {
       if (e >= n_occ) return 0u;
       const uint32_t slot = occ[e];
-      const Elem x = exact_elem(ix, a, c, keys[slot], vals[slot], denom);
-      if (x.id == kEmpty) return 0u;
-      const uint32_t fb = __float_as_uint((float)bits_score(x.s));
+      const uint32_t key = keys[slot];
+      if (key == c.last_idx) return 0u;                                    // mod.rs:157-160
+      if (a.biz && !passes_business_rules(c.cur_attr, ix.attr[key])) return 0u;
+      const double idf = ix.idf[key];
+      const float g = idf > 0.0 ? (float)idf : 1.0f;                       // mod.rs:145-152
+      const uint32_t fb = __float_as_uint((float)vals[slot] * g * rdenom);
       const uint32_t mono = (fb >> 31) ? ~fb : (fb | 0x80000000u);
       return (mono & ~kIdxMask) | e;
     };
@@ -352,7 +365,7 @@ __device__ __forceinline__ uint32_t select_topn(const IndexView& ix, const Predi
     uint32_t qn = 0;
     for (uint32_t base = (kWarps + warp) * 32; base < n_occ; base += kWarps * 32) {
       const uint32_t cand = coarse(base + lane);
-      const bool keep = cand != 0 && (cand >> kIdxBits) >= bound;
+      const bool keep = cand != 0 && (cand >> kIdxBits) + 1u >= bound;
       const uint32_t km = __ballot_sync(kFull, keep);
       if (km) {
         if (keep) queue[qn + __popc(km & ((1u << lane) - 1u))] = cand;
@@ -378,7 +391,7 @@ __device__ __forceinline__ uint32_t select_topn(const IndexView& ix, const Predi
       const uint32_t valid = __popc(__ballot_sync(kFull, best != 0));
       const uint32_t take = min(valid, N);
       bool ok = valid < 32;
-      if (!ok) ok = (__shfl_sync(kFull, best, 31) >> kIdxBits) < (__shfl_sync(kFull, best, (int)N - 1) >> kIdxBits);
+      if (!ok) ok = (__shfl_sync(kFull, best, 31) >> kIdxBits) + 1u < (__shfl_sync(kFull, best, (int)N - 1) >> kIdxBits);
       if (ok) {
         Elem x; x.s = 0; x.id = kEmpty;
         if (best != 0) { const uint32_t slot = occ[best & kIdxMask]; x = exact_elem(ix, a, c, keys[slot], vals[slot], denom); }
@@ -752,7 +765,7 @@ vmis_predict_kernel(const IndexView ix, const PredictArgs a, const LaunchPlan pl
     __syncthreads();
     // the occupied-slot list reuses the flat map's storage (dead once the inserts are done)
     uint16_t* socc = reinterpret_cast<uint16_t*>(fbits);
-    if (!S.overflow) compact_slots<uint16_t>(S, stab_keys, plan.tab_cap, socc, plan.occ_cap);
+    if (!S.overflow) compact_slots<uint16_t>(S, par, stab_keys, plan.tab_cap, socc, plan.occ_cap);
     __syncthreads();
     if (!S.overflow) {
       written = select_topn<false, uint16_t>(ix, a, S, X, c, stab_keys, stab_vals, socc, S.n_occ);
@@ -774,7 +787,7 @@ vmis_predict_kernel(const IndexView ix, const PredictArgs a, const LaunchPlan pl
       __syncthreads();
       accumulate(ix, S, fm, total_items, last_idx, gkeys, gvals, ws.gtab_cap - 1);
       __syncthreads();
-      compact_slots<uint32_t>(S, gkeys, ws.gtab_cap, gocc, ws.gtab_cap / 2);
+      compact_slots<uint32_t>(S, par, gkeys, ws.gtab_cap, gocc, ws.gtab_cap / 2);
       __syncthreads();
       const uint32_t n_occ = S.n_occ;
       written = select_topn<true, uint32_t>(ix, a, S, X, c, gkeys, gvals, gocc, n_occ);
