@@ -241,10 +241,8 @@ def main():
     clocks = sampler.stop()
     step_ms = [ev[s].elapsed_time(ev[s + 1]) for s in range(args.steps)]
     total_ms = ev[0].elapsed_time(ev[-1])
-    t = torch.tensor([total_ms], dtype=torch.float64, device=dev)
-    if world > 1:
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    total_ms_max = float(t.item())
+    from serenade_b200.shard import max_over_ranks
+    total_ms_max = max_over_ranks(total_ms, device=dev)
     value = world * args.steps * B / (total_ms_max * 1e-3)
 
     # roofline of the (single) kernel: algorithmic bytes of the timed batches / their kernel time
@@ -287,10 +285,7 @@ def main():
         e2e_call(args.warmup + s)
     torch.cuda.synchronize()
     e2e_s = time.perf_counter() - t_e0
-    t = torch.tensor([e2e_s], dtype=torch.float64, device=dev)
-    if world > 1:
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    e2e_value = world * args.steps * B / float(t.item())
+    e2e_value = world * args.steps * B / max_over_ranks(e2e_s, device=dev)
     h2d = int(np.mean([qi.numel() * 8 + qo.numel() * 4 for qi, qo in h_q[args.warmup:]]))
     d2h = B * n * 16 + B * 4
 
