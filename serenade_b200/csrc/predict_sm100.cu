@@ -221,10 +221,14 @@ struct FlatMap {
 
 constexpr uint32_t kMaxProbe = 512;        // a probe sequence this long means the table is (nearly) full
 
-__device__ __forceinline__ void accumulate(const IndexView& ix, SmemLayout& S, const FlatMap fm, uint32_t total,
-                                           uint32_t last_idx, uint32_t* keys, int32_t* vals, uint32_t mask) {
+// Returns the number of slots this WARP claimed; when kRecord, their indices are appended to the warp's own
+// segment `occ_seg` (phase 3 lets every warp score the slots it claimed, so no compaction pass is needed).
+template <bool kRecord>
+__device__ __forceinline__ uint32_t accumulate(const IndexView& ix, SmemLayout& S, const FlatMap fm, uint32_t total,
+                                               uint32_t last_idx, uint32_t* keys, int32_t* vals, uint32_t mask,
+                                               uint16_t* occ_seg, uint32_t seg_cap) {
   const uint32_t lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
-  const uint32_t le_mask = 0xFFFFFFFFu >> (31u - lane);
+  const uint32_t lt_mask = (1u << lane) - 1u, le_mask = 0xFFFFFFFFu >> (31u - lane);
   auto gather = [&](uint32_t base, uint32_t& item, int32_t& wgt) {
     item = kEmpty; wgt = 0;
     const uint32_t e = base + lane;
@@ -236,6 +240,7 @@ __device__ __forceinline__ void accumulate(const IndexView& ix, SmemLayout& S, c
       if (item == last_idx) item = kEmpty;
     }
   };
+  uint32_t wn = 0;                                   // warp-uniform count of claimed slots
   uint32_t nxt_item = kEmpty; int32_t nxt_w = 0;
   uint32_t base = warp * 32;
   if (base < total) gather(base, nxt_item, nxt_w);
@@ -248,19 +253,33 @@ __device__ __forceinline__ void accumulate(const IndexView& ix, SmemLayout& S, c
     // clustering of linear probing (shared memory has no locality to lose)
     const uint32_t hv = idx * 0x9E3779B1u;
     const uint32_t stride = ((hv >> 20) | 1u) & mask;
-    uint32_t h = (hv >> 7) & mask, steps = 0;
-    while (__any_sync(kFull, !done)) {
+    uint32_t h = (hv >> 7) & mask;
+    for (uint32_t steps = 0;; ++steps) {             // warp-converged: one probe step of every unfinished lane
+      bool claimed = false;
       if (!done) {
         uint32_t cur = *reinterpret_cast<volatile uint32_t*>(&keys[h]);
-        if (cur == kEmpty) { cur = atomicCAS(&keys[h], kEmpty, idx); if (cur == kEmpty) cur = idx; }
+        if (cur == kEmpty) {
+          cur = atomicCAS(&keys[h], kEmpty, idx);
+          if (cur == kEmpty) { claimed = true; cur = idx; }
+        }
         if (cur == idx) { atomicAdd(&vals[h], w); done = true; }
-        else {
-          h = (h + stride) & mask;
-          if (++steps > kMaxProbe) { S.overflow = 1u; done = true; }
+      }
+      if (kRecord) {
+        const uint32_t cm = __ballot_sync(kFull, claimed);
+        if (cm) {
+          if (claimed) {
+            const uint32_t n = wn + (uint32_t)__popc(cm & lt_mask);
+            if (n < seg_cap) occ_seg[n] = (uint16_t)h; else S.overflow = 1u;
+          }
+          wn += (uint32_t)__popc(cm);
         }
       }
+      if (!__any_sync(kFull, !done)) break;
+      if (steps >= kMaxProbe) { S.overflow = 1u; break; }
+      if (!done) h = (h + stride) & mask;
     }
   }
+  return min(wn, seg_cap);
 }
 
 // compaction of the occupied slots into `occ` (any order): every thread inspects the slots tid, tid+256, ...
@@ -328,14 +347,17 @@ __device__ __forceinline__ Elem exact_elem(const IndexView& ix, const PredictArg
 // packed with the entry index selects 32 candidates with a u32 warp-bitonic network; if that candidate set
 // provably contains the exact top-n (no coarse tie across its boundary) they are scored exactly and sorted
 // once.  Otherwise (how_many > 31, heavy ties, global table) the exact 96-bit network scans everything.
+// The occupied-slot list `occ` is walked per warp: entries e = e_begin + lane, + e_step, ... < e_end (shared table:
+// the warp's own segment of claimed slots; global table: the compacted list, strided over the warps).
 template <bool kGlobal, typename OccT>
 __device__ __forceinline__ uint32_t select_topn(const IndexView& ix, const PredictArgs& a, SmemLayout& S, Scratch& X,
                                                 const QueryCtx& c, const uint32_t* keys, const int32_t* vals,
-                                                const OccT* occ, uint32_t n_occ) {
+                                                const OccT* occ, uint32_t e_begin, uint32_t e_end, uint32_t e_step) {
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const uint32_t N = a.how_many, q = c.q;
   const double denom = (double)(10u * c.u);
-  if (!kGlobal && N <= 31 && n_occ <= kIdxMask) {
+  const uint32_t n_occ = e_end;                                            // bound of valid entry indices for this warp
+  if (!kGlobal && N <= 31) {
     // coarse key of entry e (0 = filtered / out of range): 19-bit monotone image of an fp32 APPROXIMATION of the
     // score (relative error < 2^-21, far below the 2^-10 coarse unit), so exact order can only disagree with
     // coarse order by one unit: every exact top-n element has coarse >= (n-th largest coarse) - 1.
@@ -353,7 +375,7 @@ __device__ __forceinline__ uint32_t select_topn(const IndexView& ix, const Predi
       return (mono & ~kIdxMask) | e;
     };
     // round 0: every warp sorts its first 32 entries; its N-th best is a lower bound of the global N-th best
-    uint32_t best = u32_sort_desc(coarse(warp * 32 + lane), lane);
+    uint32_t best = u32_sort_desc(coarse(e_begin + lane), lane);
     if (lane == 0) S.bound[warp] = __shfl_sync(kFull, best, (int)N - 1) >> kIdxBits;
     else (void)__shfl_sync(kFull, best, (int)N - 1);
     __syncthreads();
@@ -363,7 +385,7 @@ __device__ __forceinline__ uint32_t select_topn(const IndexView& ix, const Predi
     // later rounds: only entries at or above the bound can matter; they are queued and merged 32 at a time
     uint32_t* queue = X.sel.queue[warp];
     uint32_t qn = 0;
-    for (uint32_t base = (kWarps + warp) * 32; base < n_occ; base += kWarps * 32) {
+    for (uint32_t base = e_begin + e_step; base < e_end; base += e_step) {
       const uint32_t cand = coarse(base + lane);
       const bool keep = cand != 0 && (cand >> kIdxBits) + 1u >= bound;
       const uint32_t km = __ballot_sync(kFull, keep);
@@ -414,10 +436,10 @@ __device__ __forceinline__ uint32_t select_topn(const IndexView& ix, const Predi
   bool first_round = true;
   while (written < N) {
     Elem top; top.s = 0; top.id = kEmpty;
-    for (uint32_t base = warp * 32; base < n_occ; base += kWarps * 32) {
+    for (uint32_t base = e_begin; base < e_end; base += e_step) {
       const uint32_t e = base + lane;
       Elem x; x.s = 0; x.id = kEmpty;
-      if (e < n_occ) {
+      if (e < e_end) {
         const uint32_t slot = occ[e];
         x = exact_elem(ix, a, c, keys[slot], vals[slot], denom);
         if (!first_round && !better(bound, x)) { x.s = 0; x.id = kEmpty; }
@@ -474,6 +496,7 @@ vmis_predict_kernel(const IndexView ix, const PredictArgs a, const LaunchPlan pl
   int32_t* stab_vals = reinterpret_cast<int32_t*>(stab_keys + plan.tab_cap);
   uint32_t* fbits = reinterpret_cast<uint32_t*>(stab_vals + plan.tab_cap);
   uint16_t* fdir = reinterpret_cast<uint16_t*>(fbits + plan.fmap_words);
+  uint16_t* socc = fdir + plan.fmap_words;                         // kWarps segments of claimed slots
 
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const uint32_t K = a.k, M = a.m, N = a.how_many;
@@ -761,37 +784,33 @@ vmis_predict_kernel(const IndexView ix, const PredictArgs a, const LaunchPlan pl
     // occupancy budget is redone on this CTA's global table
     FlatMap fm;
     fm.bits = fbits; fm.dir = fdir; fm.start = nbr_start; fm.off4 = nbr_off4; fm.w = nbr_low;
-    accumulate(ix, S, fm, total_items, last_idx, stab_keys, stab_vals, plan.tab_cap - 1);
-    __syncthreads();
-    // the occupied-slot list reuses the flat map's storage (dead once the inserts are done)
-    uint16_t* socc = reinterpret_cast<uint16_t*>(fbits);
-    if (!S.overflow) compact_slots<uint16_t>(S, par, stab_keys, plan.tab_cap, socc, plan.occ_cap);
+    // every warp records the slots it claims in its own segment of the list and scores exactly those in phase 3
+    const uint32_t seg = plan.occ_cap / kWarps;
+    if (nn == 0 || N == 0) {
+      written = 0;
+    } else {
+    const uint32_t wn = accumulate<true>(ix, S, fm, total_items, last_idx, stab_keys, stab_vals, plan.tab_cap - 1,
+                                         socc + (size_t)warp * seg, seg);
     __syncthreads();
     if (!S.overflow) {
-      written = select_topn<false, uint16_t>(ix, a, S, X, c, stab_keys, stab_vals, socc, S.n_occ);
+      written = select_topn<false, uint16_t>(ix, a, S, X, c, stab_keys, stab_vals, socc, (uint32_t)warp * seg,
+                                             (uint32_t)warp * seg + wn, 32u);
     } else {
       // redo on this CTA's global table: big enough for every item of every neighbour, cleaned after use
       uint32_t* gkeys = ws.gtab_keys + (size_t)blockIdx.x * ws.gtab_cap;
       int32_t* gvals = ws.gtab_vals + (size_t)blockIdx.x * ws.gtab_cap;
       uint32_t* gocc = ws.gtab_occ + (size_t)blockIdx.x * (ws.gtab_cap / 2);
-      // the flat map was overwritten by the partial slot list: rebuild it
       __syncthreads();
-      for (uint32_t i = tid; i < plan.fmap_words; i += kThreads) fbits[i] = 0u;
       if (tid == 0) { S.n_occ = 0; S.overflow = 0; }
       __syncthreads();
-      for (uint32_t i = tid; i < nn; i += kThreads) {
-        const uint32_t s0 = nbr_start[i], last = nbr_start[i + 1] - 1;
-        atomicOr(&fbits[s0 >> 5], 1u << (s0 & 31u));
-        for (uint32_t wd = (s0 + 31u) >> 5; wd <= (last >> 5); ++wd) fdir[wd] = (uint16_t)i;
-      }
-      __syncthreads();
-      accumulate(ix, S, fm, total_items, last_idx, gkeys, gvals, ws.gtab_cap - 1);
+      accumulate<false>(ix, S, fm, total_items, last_idx, gkeys, gvals, ws.gtab_cap - 1, nullptr, 0u);
       __syncthreads();
       compact_slots<uint32_t>(S, par, gkeys, ws.gtab_cap, gocc, ws.gtab_cap / 2);
       __syncthreads();
       const uint32_t n_occ = S.n_occ;
-      written = select_topn<true, uint32_t>(ix, a, S, X, c, gkeys, gvals, gocc, n_occ);
+      written = select_topn<true, uint32_t>(ix, a, S, X, c, gkeys, gvals, gocc, (uint32_t)warp * 32u, n_occ, kThreads);
       for (uint32_t e = tid; e < n_occ; e += kThreads) { const uint32_t slot = gocc[e]; gkeys[slot] = kEmpty; gvals[slot] = 0; }
+    }
     }
     for (uint32_t i = written + tid; i < N; i += kThreads) {           // deterministic padding
       a.out_ids[(size_t)q * N + i] = 0; a.out_scores[(size_t)q * N + i] = 0.0;
@@ -823,10 +842,9 @@ int plan_launch(const IndexView& ix, uint32_t k, uint32_t m, int sm_count, Launc
   const size_t r1 = size_t(p.m_eff) * 16 + size_t(p.list_cap) * 8;   // two m-sample buffers + two TMA staging buffers
   p.fmap_words = (std::max(k, 1u) * std::max(ix.max_len, 1u) + 31u) / 32u + 1u;
   if (p.fmap_words > 65535u) return VMIS_ERR_LIMIT;
-  // tail of the table region: the flat map during the inserts, the occupied-slot list (u16) afterwards
-  const size_t tail = std::max(size_t(p.fmap_words) * 6 + 4, size_t(p.tab_cap / 2 + p.tab_cap / 4) * 2);
-  p.occ_cap = (uint32_t)std::min<size_t>(tail / 2, p.tab_cap);
-  const size_t r2 = size_t(p.tab_cap) * 8 + tail + 8;
+  // tail of the table region: the flat map and the per-warp lists of claimed slots (u16)
+  p.occ_cap = (p.tab_cap / 2 + p.tab_cap / 8) / kWarps * kWarps;          // 62.5 % of the slots, split over the warps
+  const size_t r2 = size_t(p.tab_cap) * 8 + size_t(p.fmap_words) * 6 + size_t(p.occ_cap) * 2 + 8;
   const size_t total = fixed + nbr + std::max(std::max(r1, r2), size_t(kMaxSessionLen) * 8) + 16;
   if (total > 227 * 1024) return VMIS_ERR_LIMIT;
   p.smem_bytes = (uint32_t)total;
