@@ -119,6 +119,9 @@ def main():
     ap.add_argument("--batch", type=int, default=1 << 20, help="evolving sessions per step (per GPU)")
     ap.add_argument("--cpu-seconds", type=float, default=15.0, help="CPU baseline sample budget")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--sharded", action="store_true",
+                    help="multi-GPU only: item-shard the postings over the ranks (config 5 layout, remote lists read "
+                         "over NVLink inside the kernel) instead of replicating the index")
     args = ap.parse_args()
     if args.warmup < 3 and args.impl == "b200":
         log("note: --warmup < 3 breaks the timing rules; use >= 3 for a reported number")
@@ -185,7 +188,12 @@ def main():
     items, off, ts = sb.synth_sessions(42, n_items, n_sessions)
     cfg["interactions"] = int(len(items))
     t1 = time.time()
-    gix = sb.VMISIndex.from_sessions(items, off, ts, M, MAX_LEN, IDF_W, device=local_rank)
+    if args.sharded and world > 1:
+        gix = sb.VMISIndex.from_sessions_sharded(items, off, ts, M, MAX_LEN, IDF_W, local_rank, rank, world)
+        gix.connect_shards(rank, world)
+        cfg["parallelism"] = f"item-sharded postings x{world} (peer HBM over NVLink, CUDA IPC), queries sharded"
+    else:
+        gix = sb.VMISIndex.from_sessions(items, off, ts, M, MAX_LEN, IDF_W, device=local_rank)
     st = gix.stats()
     log(f"[rank {rank}] synth {t1 - t0:.1f}s, index build+upload {time.time() - t1:.1f}s, "
         f"{st['device_bytes'] / 1e6:.0f} MB in HBM, {st['n_items']} items, {st['n_postings']} postings")

@@ -83,6 +83,22 @@ vmis_index_t* vmis_index_from_csv_ex(const char* path, size_t m, double idf_weig
 vmis_index_t* vmis_index_from_sessions(const uint64_t* items, const uint64_t* sess_off, const uint32_t* sess_ts,
                                        size_t n_sessions, size_t m, size_t max_len, double idf_weighting, int device);
 
+/* ---- item-sharded postings (BASELINE.json config 5; no counterpart in the reference, which replicates) ----
+ * The item→sessions index is partitioned over the GPUs of one box: shard s of n holds the posting lists of the
+ * items whose dense index % n == s; the session→items lists, idf and attributes are replicated.  Every process
+ * builds its shard, exports it (CUDA IPC handle, 64 bytes), and attaches the shards of its peers; the predict
+ * kernel then streams remote posting lists over NVLink inside the same launch (TMA bulk copies / loads on the
+ * peer-mapped pointers), so results are bit-identical to the single-GPU index and there is no separate
+ * exchange step.  Queries may be sharded over the ranks in any way. */
+vmis_index_t* vmis_index_from_sessions_sharded(const uint64_t* items, const uint64_t* sess_off, const uint32_t* sess_ts,
+                                               size_t n_sessions, size_t m, size_t max_len, double idf_weighting,
+                                               int device, uint32_t shard, uint32_t n_shards);
+int vmis_index_export_shard(const vmis_index_t* index, void* handle64);
+int vmis_index_attach_shard(vmis_index_t* index, uint32_t shard, const void* handle64);
+/* same-process variant (several shards on GPUs of one process, or on one GPU in tests) */
+int vmis_index_attach_shard_ptr(vmis_index_t* index, uint32_t shard, const void* device_ptr);
+const void* vmis_index_shard_ptr(const vmis_index_t* index);
+
 /* item_to_product_attributes (vmis_index.rs:34; Avro fields ForSale/IsAdult :184-192).  Replaces the
  * attributes of the listed items (flags = VMIS_ATTR_* bits; 0 removes the entry).  Call before serving. */
 int vmis_index_set_attributes(vmis_index_t* index, const uint64_t* items, const uint8_t* flags, size_t n);

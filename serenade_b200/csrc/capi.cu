@@ -58,6 +58,8 @@ struct vmis_index {
   std::vector<void*> dev_allocs;
   uint64_t device_bytes = 0;
   uint64_t n_sessions_kept = 0;
+  uint32_t shard = 0;                        // item-sharded postings: the shard this handle owns
+  std::vector<void*> ipc_mapped;             // peer shards opened through CUDA IPC
   std::mutex mu;
   std::vector<std::unique_ptr<CallCtx>> pool;
 };
@@ -91,24 +93,33 @@ int select_device(int device, int* sm_count) {
   return VMIS_OK;
 }
 
-vmis_index* finish_index(std::unique_ptr<vmis_index> ix, size_t m, size_t max_len, double idf_w, int device) {
+vmis_index* finish_index(std::unique_ptr<vmis_index> ix, size_t m, size_t max_len, double idf_w, int device,
+                         uint32_t shard = 0, uint32_t n_shards = 1) {
   std::string err;
+  if (n_shards == 0 || shard >= n_shards) { fail(VMIS_ERR_ARG, "shard %u out of range [0,%u)", shard, n_shards); return nullptr; }
   if (max_len == 0) max_len = vmis::session_length_p99_5(ix->sessions);
-  if (!vmis::build_flat_index(ix->sessions, m, max_len, idf_w, &ix->flat, &err)) { fail(VMIS_ERR_ARG, "%s", err.c_str()); return nullptr; }
+  if (!vmis::build_flat_index(ix->sessions, m, max_len, idf_w, n_shards, &ix->flat, &err)) { fail(VMIS_ERR_ARG, "%s", err.c_str()); return nullptr; }
+  ix->shard = shard;
   ix->n_sessions_kept = ix->flat.rank_to_orig.size();
   ix->device = device;
   if (device == VMIS_DEVICE_NONE) return ix.release();   // host-only handle: accessors work, queries fail
   if (select_device(device, &ix->sm_count) != VMIS_OK) return nullptr;
   vmis::FlatIndex& F = ix->flat;
   vmis::IndexView& V = ix->view;
+  // only this handle's shard of the postings goes to its HBM; peers are attached later over NVLink
+  std::vector<uint32_t> own(F.postings.begin() + F.shard_begin[shard], F.postings.begin() + F.shard_begin[shard + 1]);
+  const uint32_t* own_dev = nullptr;
+  for (int s2 = 0; s2 < vmis::kMaxShards; ++s2) V.post_shard[s2] = nullptr;
+  V.n_shards = n_shards;
   if (upload(ix.get(), F.item_key, &V.item_key) || upload(ix.get(), F.item_hash, &V.item_hash) ||
-      upload(ix.get(), F.post_ref, &V.post_ref) || upload(ix.get(), F.postings, &V.postings) ||
+      upload(ix.get(), F.post_ref, &V.post_ref) || upload(ix.get(), own, &own_dev) ||
       upload(ix.get(), F.sess_ref, &V.sess_ref) || upload(ix.get(), F.sess_items, &V.sess_items) ||
       upload(ix.get(), F.idf, &V.idf) || upload(ix.get(), F.attr, &V.attr) ||
       upload(ix.get(), F.rank_to_orig, &V.rank_to_orig)) {
     for (void* d : ix->dev_allocs) cudaFree(d);
     return nullptr;
   }
+  V.post_shard[shard] = own_dev;
   V.item_hash_mask = (uint32_t)F.item_hash.size() - 1;
   V.n_items = (uint32_t)F.item_key.size();
   V.n_kept = (uint32_t)F.rank_to_orig.size();
@@ -150,6 +161,8 @@ int check_common(const vmis_index* ix, uint32_t k, uint32_t m, vmis::LaunchPlan*
   if (!ix) return fail(VMIS_ERR_ARG, "index is NULL");
   if (ix->device == VMIS_DEVICE_NONE)
     return fail(VMIS_ERR_CUDA, "host-only index (VMIS_DEVICE_NONE): queries need a B200; there is no CPU fallback");
+  for (uint32_t s2 = 0; s2 < ix->view.n_shards; ++s2)
+    if (!ix->view.post_shard[s2]) return fail(VMIS_ERR_ARG, "posting shard %u of %u is not attached", s2, ix->view.n_shards);
   const int rc = vmis::plan_launch(ix->view, k, m, ix->sm_count, plan);
   if (rc != VMIS_OK)
     return fail(rc, "k=%u / m=%u beyond kernel limits (k <= %u, m <= %u and shared memory)", k, m, vmis::kMaxK, vmis::kMaxM);
@@ -252,6 +265,52 @@ vmis_index_t* vmis_index_from_sessions(const uint64_t* items, const uint64_t* se
   return finish_index(std::move(ix), m, max_len, idf_weighting, device);
 }
 
+vmis_index_t* vmis_index_from_sessions_sharded(const uint64_t* items, const uint64_t* sess_off, const uint32_t* sess_ts,
+                                               size_t n_sessions, size_t m, size_t max_len, double idf_weighting,
+                                               int device, uint32_t shard, uint32_t n_shards) {
+  if (!sess_off || !sess_ts || (!items && n_sessions && sess_off[n_sessions] > 0)) { fail(VMIS_ERR_ARG, "NULL session arrays"); return nullptr; }
+  std::unique_ptr<vmis_index> ix(new vmis_index());
+  ix->sessions.off.assign(sess_off, sess_off + n_sessions + 1);
+  ix->sessions.ts.assign(sess_ts, sess_ts + n_sessions);
+  ix->sessions.items.assign(items, items + sess_off[n_sessions]);
+  return finish_index(std::move(ix), m, max_len, idf_weighting, device, shard, n_shards);
+}
+
+int vmis_index_export_shard(const vmis_index_t* ix, void* handle64) {
+  if (!ix || !handle64 || ix->device == VMIS_DEVICE_NONE) return fail(VMIS_ERR_ARG, "no device shard to export");
+  static_assert(sizeof(cudaIpcMemHandle_t) == 64, "IPC handle size");
+  CU_TRY(cudaSetDevice(ix->device));
+  cudaIpcMemHandle_t h;
+  CU_TRY(cudaIpcGetMemHandle(&h, const_cast<uint32_t*>(ix->view.post_shard[ix->shard])));
+  std::memcpy(handle64, &h, 64);
+  return VMIS_OK;
+}
+
+int vmis_index_attach_shard(vmis_index_t* ix, uint32_t shard, const void* handle64) {
+  if (!ix || !handle64 || ix->device == VMIS_DEVICE_NONE) return fail(VMIS_ERR_ARG, "NULL argument");
+  if (shard >= ix->view.n_shards || shard == ix->shard) return fail(VMIS_ERR_ARG, "cannot attach shard %u", shard);
+  CU_TRY(cudaSetDevice(ix->device));
+  cudaIpcMemHandle_t h;
+  std::memcpy(&h, handle64, 64);
+  void* p = nullptr;
+  CU_TRY(cudaIpcOpenMemHandle(&p, h, cudaIpcMemLazyEnablePeerAccess));
+  ix->ipc_mapped.push_back(p);
+  ix->view.post_shard[shard] = static_cast<const uint32_t*>(p);
+  return VMIS_OK;
+}
+
+int vmis_index_attach_shard_ptr(vmis_index_t* ix, uint32_t shard, const void* device_ptr) {
+  if (!ix || !device_ptr || ix->device == VMIS_DEVICE_NONE) return fail(VMIS_ERR_ARG, "NULL argument");
+  if (shard >= ix->view.n_shards || shard == ix->shard) return fail(VMIS_ERR_ARG, "cannot attach shard %u", shard);
+  ix->view.post_shard[shard] = static_cast<const uint32_t*>(device_ptr);
+  return VMIS_OK;
+}
+
+const void* vmis_index_shard_ptr(const vmis_index_t* ix) {
+  if (!ix || ix->device == VMIS_DEVICE_NONE) return nullptr;
+  return ix->view.post_shard[ix->shard];
+}
+
 vmis_index_t* vmis_index_from_csv_ex(const char* path, size_t m, double idf_weighting, size_t max_len, int device) {
   if (!path) { fail(VMIS_ERR_ARG, "path is NULL"); return nullptr; }
   std::unique_ptr<vmis_index> ix(new vmis_index());
@@ -284,6 +343,7 @@ void vmis_index_free(vmis_index_t* ix) {
   cudaSetDevice(ix->device);
   cudaDeviceSynchronize();
   ix->pool.clear();
+  for (void* p : ix->ipc_mapped) cudaIpcCloseMemHandle(p);
   for (void* d : ix->dev_allocs) cudaFree(d);
   delete ix;
 }
@@ -377,7 +437,8 @@ size_t vmis_postings(const vmis_index_t* ix, uint64_t item, uint32_t* out, size_
   if (d == vmis::kEmpty) return 0;
   const uint2 ref = ix->flat.post_ref[d];
   if (ix->flat.postings.empty()) { fail(VMIS_ERR_ARG, "postings live in HBM only; use a VMIS_DEVICE_NONE handle to inspect them"); return ref.y; }
-  for (size_t i = 0; i < ref.y && i < cap; ++i) out[i] = ix->flat.rank_to_orig[ix->flat.postings[(size_t)ref.x * 4 + i]];
+  const size_t base = ix->flat.shard_begin[d % ix->flat.n_shards] + (size_t)ref.x * 4;
+  for (size_t i = 0; i < ref.y && i < cap; ++i) out[i] = ix->flat.rank_to_orig[ix->flat.postings[base + i]];
   return ref.y;
 }
 

@@ -167,16 +167,18 @@ uint32_t host_lookup_item(const FlatIndex& f, uint64_t item) {
   }
 }
 
-bool build_flat_index(const Sessions& s, size_t m, size_t max_len, double idf_weighting, FlatIndex* out,
-                      std::string* err) {
+bool build_flat_index(const Sessions& s, size_t m, size_t max_len, double idf_weighting, uint32_t n_shards,
+                      FlatIndex* out, std::string* err) {
   const size_t S = s.size();
   if (S >= 0xFFFFFFFFull) { *err = "too many sessions"; return false; }
   if (m == 0) { *err = "m must be >= 1"; return false; }
+  if (n_shards == 0 || n_shards > (uint32_t)kMaxShards) { *err = "n_shards must be in [1, 8]"; return false; }
   FlatIndex& F = *out;
   F = FlatIndex();
   F.m_build = (uint32_t)std::min<size_t>(m, 0xFFFFFFFFu);
   F.max_len = (uint32_t)std::min<size_t>(max_len, 0xFFFFFFFFu);
   F.idf_weighting = idf_weighting;
+  F.n_shards = n_shards;
 
   // 1. kept sessions (len <= max_len, :452) ranked by (timestamp, session idx) ascending.  The rank
   //    replaces the timestamp: "more recent" == "larger rank", ties broken like the stable sort +
@@ -242,14 +244,19 @@ bool build_flat_index(const Sessions& s, size_t m, size_t max_len, double idf_we
   // 4. postings: per item the min(df, m) most recent kept sessions, rank descending (:497-504)
   F.post_ref.resize(I);
   {
-    uint64_t pos = 0;
+    // item d belongs to shard d % n_shards; offsets are relative to the shard's own array
+    std::vector<uint64_t> shard_size(n_shards, 0);
     for (size_t d = 0; d < I; ++d) {
       const uint32_t len = (uint32_t)std::min<uint64_t>(df[by_key[d]], m);
-      if ((pos >> 2) > 0xFFFFFFFFull) { *err = "posting array too large"; return false; }
-      F.post_ref[d] = make_uint2((uint32_t)(pos >> 2), len);
+      uint64_t& sz = shard_size[d % n_shards];
+      if ((sz >> 2) > 0xFFFFFFFFull) { *err = "posting array too large"; return false; }
+      F.post_ref[d] = make_uint2((uint32_t)(sz >> 2), len);
       F.n_postings += len;
-      pos += (len + 3u) & ~3u;
+      sz += (len + 3u) & ~3u;
     }
+    F.shard_begin.assign(n_shards + 1, 0);
+    for (uint32_t sh = 0; sh < n_shards; ++sh) F.shard_begin[sh + 1] = F.shard_begin[sh] + shard_size[sh];
+    const uint64_t pos = F.shard_begin[n_shards];
     F.postings.assign(pos, kEmpty);
     std::vector<uint32_t> fill(I, 0);
     for (size_t r = Sk; r-- > 0;) {
@@ -257,7 +264,8 @@ bool build_flat_index(const Sessions& s, size_t m, size_t max_len, double idf_we
       const uint32_t* it = &F.sess_items[(size_t)ref.x * 4];
       for (uint32_t t = 0; t < ref.y; ++t) {
         const uint32_t d = it[t];
-        if (fill[d] < F.post_ref[d].y) F.postings[(size_t)F.post_ref[d].x * 4 + fill[d]++] = (uint32_t)r;
+        if (fill[d] < F.post_ref[d].y)
+          F.postings[F.shard_begin[d % n_shards] + (size_t)F.post_ref[d].x * 4 + fill[d]++] = (uint32_t)r;
       }
     }
   }

@@ -189,6 +189,12 @@ __host__ __device__ inline size_t nbr_bytes(uint32_t k) {
   return (b + 15) & ~size_t(15);
 }
 
+// start of an item's posting list: local HBM, or a peer GPU's HBM over NVLink when the index is item-sharded
+__device__ __forceinline__ const uint32_t* posting_list(const IndexView& ix, uint32_t item_idx, uint32_t off4) {
+  const uint32_t s = ix.n_shards > 1 ? item_idx % ix.n_shards : 0u;
+  return ix.post_shard[s] + (size_t)off4 * 4;
+}
+
 struct QueryCtx {
   uint32_t q, u, last_idx, cur_attr;
 };
@@ -554,7 +560,7 @@ vmis_predict_kernel(const IndexView ix, const PredictArgs a, const LaunchPlan pl
       // ---------------------------------------------------------------- phase 1
       const uint2 ref0 = ix.post_ref[S.d_idx[0]];
       const uint32_t n0 = min(ref0.y, M);
-      const uint32_t* P0 = ix.postings + (size_t)ref0.x * 4;
+      const uint32_t* P0 = posting_list(ix, S.d_idx[0], ref0.x);
       const uint32_t low0 = (S.d_pos[0] << 24) | (L - S.d_pos[0]);
       postings_visited = n0;
       if (nd == 1) {
@@ -569,7 +575,7 @@ vmis_predict_kernel(const IndexView ix, const PredictArgs a, const LaunchPlan pl
           const uint2 ref = ix.post_ref[S.d_idx[j]];
           const uint32_t bytes = ((min(min(ref.y, M), plan.list_cap) + 3u) & ~3u) * 4u;
           mbar_expect_tx(&S.bar[b], bytes);
-          bulk_load(listbuf + (size_t)b * plan.list_cap, ix.postings + (size_t)ref.x * 4, bytes, &S.bar[b]);
+          bulk_load(listbuf + (size_t)b * plan.list_cap, posting_list(ix, S.d_idx[j], ref.x), bytes, &S.bar[b]);
         };
         if (tid == 0) { fence_async_proxy(); issue(1, 0); if (nd > 2) issue(2, 1); }
         for (uint32_t i = tid; i < n0; i += kThreads) acc[i] = ((uint64_t)P0[i] << 32) | low0;

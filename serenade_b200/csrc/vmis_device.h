@@ -15,6 +15,7 @@ constexpr int kWarps = kThreads / 32;
 constexpr int kMaxSessionLen = 128;      // evolving-session length limit of the kernel (reference HPO grid: <= 100)
 constexpr uint32_t kMaxK = 2048;         // keeps the int32 item numerators exact
 constexpr uint32_t kMaxM = 8192;         // shared-memory bound of the m-sample buffers
+constexpr int kMaxShards = 8;            // item-sharded postings: one shard per GPU of a box
 
 // ext item id -> dense item index; open addressing, val == kEmpty marks a free slot
 struct alignas(16) ItemHashEntry {
@@ -26,7 +27,8 @@ struct alignas(16) ItemHashEntry {
 // HBM layout (all arrays immutable after build):
 //   item dictionary   item_key[I] ascending external ids; dense index = rank, so
 //                     (score desc, dense idx asc) == (score desc, item_id asc)
-//   postings          per item: kept-session TIME RANKS, descending (most recent first),
+//   postings          (optionally sharded by item over the GPUs of a box, see post_shard)
+//                     per item: kept-session TIME RANKS, descending (most recent first),
 //                     truncated to m_build, list start aligned to 16 B
 //                     (replaces item_to_top_sessions_ordered + the session_to_max_time_stamp
 //                     gather of vmis_index.rs:359: rank order == (ts, session idx) order)
@@ -39,7 +41,8 @@ struct IndexView {
   const ItemHashEntry* item_hash;
   uint32_t item_hash_mask;
   const uint2* post_ref;      // {offset in units of 4 entries, length}
-  const uint32_t* postings;
+  const uint32_t* post_shard[kMaxShards];   // posting arrays; shard s holds the lists of items with dense idx % n_shards == s
+  uint32_t n_shards;                        // 1 = everything local; >1 = peers mapped over NVLink (CUDA IPC)
   const uint2* sess_ref;      // {offset in units of 4 entries, length}
   const uint32_t* sess_items;
   const double* idf;

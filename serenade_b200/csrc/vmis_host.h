@@ -25,7 +25,9 @@ struct FlatIndex {
   std::vector<uint64_t> item_key;
   std::vector<ItemHashEntry> item_hash;
   std::vector<uint2> post_ref;
-  std::vector<uint32_t> postings;
+  std::vector<uint32_t> postings;          // all shards back to back; shard s starts at shard_begin[s]
+  std::vector<uint64_t> shard_begin;       // n_shards + 1 offsets into postings (post_ref offsets are shard relative)
+  uint32_t n_shards = 1;
   std::vector<uint2> sess_ref;
   std::vector<uint32_t> sess_items;
   std::vector<double> idf;
@@ -46,8 +48,8 @@ bool read_sessions_from_csv(const std::string& path, Sessions* out, std::string*
 size_t session_length_p99_5(const Sessions& s);
 
 // prepare_hashmap (vmis_index.rs:422-528) → flat CSR arrays.
-bool build_flat_index(const Sessions& s, size_t m, size_t max_len, double idf_weighting, FlatIndex* out,
-                      std::string* err);
+bool build_flat_index(const Sessions& s, size_t m, size_t max_len, double idf_weighting, uint32_t n_shards,
+                      FlatIndex* out, std::string* err);
 
 // dense index of an external item id, kEmpty if unknown
 uint32_t host_lookup_item(const FlatIndex& f, uint64_t item);

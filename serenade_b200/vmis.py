@@ -50,6 +50,11 @@ def load_library():
         "vmis_index_from_csv": (vp, [C.c_char_p, sz, f64, i32]),
         "vmis_index_from_csv_ex": (vp, [C.c_char_p, sz, f64, sz, i32]),
         "vmis_index_from_sessions": (vp, [_u64p, _u64p, _u32p, sz, sz, sz, f64, i32]),
+        "vmis_index_from_sessions_sharded": (vp, [_u64p, _u64p, _u32p, sz, sz, sz, f64, i32, u32, u32]),
+        "vmis_index_export_shard": (i32, [vp, vp]),
+        "vmis_index_attach_shard": (i32, [vp, u32, vp]),
+        "vmis_index_attach_shard_ptr": (i32, [vp, u32, vp]),
+        "vmis_index_shard_ptr": (vp, [vp]),
         "vmis_index_set_attributes": (i32, [vp, _u64p, _u8p, sz]),
         "vmis_index_free": (None, [vp]),
         "vmis_index_stats": (i32, [vp, C.POINTER(_Stats)]),
@@ -76,6 +81,8 @@ def load_library():
 
 
 EXPORTED_SYMBOLS = ("vmis_index_from_csv", "vmis_index_from_csv_ex", "vmis_index_from_sessions",
+                    "vmis_index_from_sessions_sharded", "vmis_index_export_shard", "vmis_index_attach_shard",
+                    "vmis_index_attach_shard_ptr", "vmis_index_shard_ptr",
                     "vmis_index_set_attributes", "vmis_index_free", "vmis_index_stats", "vmis_predict_batch",
                     "vmis_predict_batch_device", "vmis_predict", "vmis_find_neighbors_batch", "vmis_items_for_session",
                     "vmis_idf", "vmis_find_attributes", "vmis_postings", "vmis_session_timestamp",
@@ -128,6 +135,42 @@ class VMISIndex:
         return cls(L.vmis_index_from_sessions(_p(items, C.c_uint64), _p(sess_off, C.c_uint64),
                                               _p(sess_ts, C.c_uint32), len(sess_ts), m_most_recent_sessions, max_len,
                                               float(idf_weighting), device))
+
+    @classmethod
+    def from_sessions_sharded(cls, items, sess_off, sess_ts, m_most_recent_sessions, max_len, idf_weighting, device,
+                              shard, n_shards):
+        """Item-sharded postings (BASELINE config 5): this handle owns shard `shard` of `n_shards`; attach the
+        peers with connect_shards() (one process per GPU) or attach_shard_ptr() (same process)."""
+        L = load_library()
+        items = np.ascontiguousarray(items, dtype=np.uint64)
+        sess_off = np.ascontiguousarray(sess_off, dtype=np.uint64)
+        sess_ts = np.ascontiguousarray(sess_ts, dtype=np.uint32)
+        return cls(L.vmis_index_from_sessions_sharded(_p(items, C.c_uint64), _p(sess_off, C.c_uint64),
+                                                      _p(sess_ts, C.c_uint32), len(sess_ts), m_most_recent_sessions,
+                                                      max_len, float(idf_weighting), device, shard, n_shards))
+
+    def export_shard(self):
+        buf = C.create_string_buffer(64)
+        _check(load_library().vmis_index_export_shard(self._h, buf))
+        return buf.raw
+
+    def attach_shard(self, shard, handle_bytes):
+        _check(load_library().vmis_index_attach_shard(self._h, shard, C.create_string_buffer(handle_bytes, 64)))
+
+    def attach_shard_ptr(self, shard, device_ptr):
+        _check(load_library().vmis_index_attach_shard_ptr(self._h, shard, C.c_void_p(device_ptr)))
+
+    def shard_ptr(self):
+        return load_library().vmis_index_shard_ptr(self._h)
+
+    def connect_shards(self, rank, world, group=None):
+        """exchange the CUDA IPC handles of all ranks' shards through torch.distributed and attach the peers"""
+        import torch.distributed as dist
+        handles = [None] * world
+        dist.all_gather_object(handles, self.export_shard(), group=group)
+        for s, h in enumerate(handles):
+            if s != rank:
+                self.attach_shard(s, h)
 
     def close(self):
         if getattr(self, "_h", None) and _lib is not None:

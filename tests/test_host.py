@@ -167,3 +167,18 @@ def test_argument_errors(sb):
     assert hix.find_attributes(int(items[0])) == {"is_for_sale": True, "is_adult": True}
     hix.set_attributes(np.array([int(items[0])], dtype=np.uint64), np.array([0], dtype=np.uint8))
     assert hix.find_attributes(int(items[0])) is None
+
+
+def test_sharded_posting_layout_matches_unsharded(sb):
+    """item-sharded postings (config 5): same lists whichever shard an item lands in"""
+    items, off, ts = random_index_data(np.random.default_rng(8), 500, 40, max_len=7)
+    full = sb.VMISIndex.from_sessions(items, off, ts, 25, 7, 1.0, device=sb.DEVICE_NONE)
+    for n_shards in (2, 3, 8):
+        sh = sb.VMISIndex.from_sessions_sharded(items, off, ts, 25, 7, 1.0, sb.DEVICE_NONE, 0, n_shards)
+        assert sh.stats()["n_postings"] == full.stats()["n_postings"]
+        for it in np.unique(items):
+            assert np.array_equal(sh.postings(int(it)), full.postings(int(it)))
+    with pytest.raises(sb.VmisError):
+        sb.VMISIndex.from_sessions_sharded(items, off, ts, 25, 7, 1.0, sb.DEVICE_NONE, 2, 2)
+    with pytest.raises(sb.VmisError):
+        sb.VMISIndex.from_sessions_sharded(items, off, ts, 25, 7, 1.0, sb.DEVICE_NONE, 0, 9)
