@@ -33,7 +33,11 @@ WORKLOADS = {
     # name: (n_items, n_sessions)  — sessions chosen so that interactions hit the config's figure
     "synthetic-1M-50k": (50_000, 193_000),
     "synthetic-60M-1.76M": (1_760_000, 11_556_000),
+    # configs 4-5: generated and indexed on the device (vmis_index_synth); no CPU arm at these sizes
+    "synthetic-582M-6.5M": (6_500_000, 112_100_000),
+    "synthetic-2.3B-6.5M": (6_500_000, 443_000_000),
 }
+DEVICE_BUILT = {"synthetic-582M-6.5M", "synthetic-2.3B-6.5M"}
 K, M, HOW_MANY, MAX_ITEMS, IDF_W, MAX_LEN = 288, 1502, 21, 4, 2.0, 34
 METRIC = "predict_next queries/sec @ k=288,m=1502"
 
@@ -119,6 +123,7 @@ def main():
     ap.add_argument("--batch", type=int, default=1 << 20, help="evolving sessions per step (per GPU)")
     ap.add_argument("--cpu-seconds", type=float, default=15.0, help="CPU baseline sample budget")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--device-build", action="store_true", help="generate + index the workload on the device")
     ap.add_argument("--sharded", action="store_true",
                     help="multi-GPU only: item-shard the postings over the ranks (config 5 layout, remote lists read "
                          "over NVLink inside the kernel) instead of replicating the index")
@@ -185,15 +190,25 @@ def main():
     lib = sb.load_library()
 
     t0 = time.time()
-    items, off, ts = sb.synth_sessions(42, n_items, n_sessions)
-    cfg["interactions"] = int(len(items))
-    t1 = time.time()
-    if args.sharded and world > 1:
-        gix = sb.VMISIndex.from_sessions_sharded(items, off, ts, M, MAX_LEN, IDF_W, local_rank, rank, world)
+    device_built = args.workload in DEVICE_BUILT or args.device_build
+    shard_args = (rank, world) if (args.sharded and world > 1) else (0, 1)
+    if device_built:
+        items = off = ts = None
+        t1 = time.time()
+        gix = sb.VMISIndex.synth(42, n_items, n_sessions, M, MAX_LEN, IDF_W, local_rank, *shard_args)
+        cfg["interactions"] = int(gix.stats()["n_pairs_kept"])
+        cfg["index_build"] = "generated and indexed on the device (vmis_index_synth)"
+    else:
+        items, off, ts = sb.synth_sessions(42, n_items, n_sessions)
+        cfg["interactions"] = int(len(items))
+        t1 = time.time()
+        if shard_args[1] > 1:
+            gix = sb.VMISIndex.from_sessions_sharded(items, off, ts, M, MAX_LEN, IDF_W, local_rank, *shard_args)
+        else:
+            gix = sb.VMISIndex.from_sessions(items, off, ts, M, MAX_LEN, IDF_W, device=local_rank)
+    if shard_args[1] > 1:
         gix.connect_shards(rank, world)
         cfg["parallelism"] = f"item-sharded postings x{world} (peer HBM over NVLink, CUDA IPC), queries sharded"
-    else:
-        gix = sb.VMISIndex.from_sessions(items, off, ts, M, MAX_LEN, IDF_W, device=local_rank)
     st = gix.stats()
     log(f"[rank {rank}] synth {t1 - t0:.1f}s, index build+upload {time.time() - t1:.1f}s, "
         f"{st['device_bytes'] / 1e6:.0f} MB in HBM, {st['n_items']} items, {st['n_postings']} postings")
@@ -304,7 +319,7 @@ def main():
            "e2e": {"value": e2e_value, "unit": "queries/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h},
            "roofline": roofline, "step_ms": [round(x, 3) for x in step_ms]}
 
-    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+    if rank == 0 and world == 1 and not args.no_cpu_baseline and items is not None:
         from oracle import vmis_oracle as vo
         t2 = time.time()
         oix = vo.OracleIndex.from_sessions(items, off, ts, M, MAX_LEN, IDF_W)

@@ -99,6 +99,17 @@ int vmis_index_attach_shard(vmis_index_t* index, uint32_t shard, const void* han
 int vmis_index_attach_shard_ptr(vmis_index_t* index, uint32_t shard, const void* device_ptr);
 const void* vmis_index_shard_ptr(const vmis_index_t* index);
 
+/* ---- on-device index build (prepare_hashmap, vmis_index.rs:422-528, as radix sorts + kernels) ------------
+ * Training sessions already resident in HBM (e.g. produced by another GPU job); max_len must be explicit.
+ * The resulting handle has no host mirror of the sessions: vmis_items_for_session / vmis_session_timestamp fail,
+ * every other entry point works.  Results are bit-identical to the host-built index. */
+vmis_index_t* vmis_index_from_device_sessions(const uint64_t* d_items, const uint64_t* d_sess_off, const uint32_t* d_sess_ts,
+                                              size_t n_sessions, size_t m, size_t max_len, double idf_weighting, int device,
+                                              uint32_t shard, uint32_t n_shards);
+/* vmis_synth_sessions generated and indexed entirely on the device (BASELINE configs 4-5). */
+vmis_index_t* vmis_index_synth(uint64_t seed, uint64_t n_items, uint64_t n_sessions, size_t m, size_t max_len,
+                               double idf_weighting, int device, uint32_t shard, uint32_t n_shards);
+
 /* item_to_product_attributes (vmis_index.rs:34; Avro fields ForSale/IsAdult :184-192).  Replaces the
  * attributes of the listed items (flags = VMIS_ATTR_* bits; 0 removes the entry).  Call before serving. */
 int vmis_index_set_attributes(vmis_index_t* index, const uint64_t* items, const uint8_t* flags, size_t n);

@@ -13,6 +13,7 @@
 #include <string>
 #include <vector>
 
+#include "build_device.h"
 #include "vmis_host.h"
 
 namespace {
@@ -59,6 +60,7 @@ struct vmis_index {
   uint64_t device_bytes = 0;
   uint64_t n_sessions_kept = 0;
   uint32_t shard = 0;                        // item-sharded postings: the shard this handle owns
+  uint64_t synth_interactions = 0;           // vmis_index_synth: interactions generated on the device
   std::vector<void*> ipc_mapped;             // peer shards opened through CUDA IPC
   std::mutex mu;
   std::vector<std::unique_ptr<CallCtx>> pool;
@@ -129,6 +131,28 @@ vmis_index* finish_index(std::unique_ptr<vmis_index> ix, size_t m, size_t max_le
   std::vector<uint32_t>().swap(F.postings);
   std::vector<uint32_t>().swap(F.sess_items);
   std::vector<uint2>().swap(F.sess_ref);
+  return ix.release();
+}
+
+// wrap the arrays of an on-device build into a handle
+vmis_index* adopt_device_index(std::unique_ptr<vmis_index> ix, vmis::DeviceIndexArrays& A, size_t m, size_t max_len,
+                               double idf_w, int device, uint32_t shard, uint32_t n_shards) {
+  vmis::FlatIndex& F = ix->flat;
+  F.item_key.swap(A.host_item_key); F.item_hash.swap(A.host_item_hash); F.idf.swap(A.host_idf);
+  F.attr.assign(A.n_items, (uint8_t)(VMIS_ATTR_EXISTS | VMIS_ATTR_FOR_SALE));
+  F.n_pairs_kept = A.n_pairs_kept; F.n_postings = A.n_postings; F.n_shards = n_shards;
+  F.m_build = (uint32_t)std::min<size_t>(m, 0xFFFFFFFFu); F.max_len = (uint32_t)max_len; F.idf_weighting = idf_w;
+  ix->n_sessions_kept = A.n_kept; ix->device = device; ix->shard = shard;
+  vmis::IndexView& V = ix->view;
+  for (int s2 = 0; s2 < vmis::kMaxShards; ++s2) V.post_shard[s2] = nullptr;
+  V.item_key = A.item_key; V.item_hash = A.item_hash; V.item_hash_mask = (uint32_t)(A.item_hash_cap - 1);
+  V.post_ref = A.post_ref; V.post_shard[shard] = A.postings; V.n_shards = n_shards;
+  V.sess_ref = A.sess_ref; V.sess_items = A.sess_items; V.idf = A.idf; V.attr = A.attr; V.rank_to_orig = A.rank_to_orig;
+  V.n_items = (uint32_t)A.n_items; V.n_kept = (uint32_t)A.n_kept; V.m_build = F.m_build; V.max_len = F.max_len;
+  void* owned[] = {A.item_key, A.item_hash, A.post_ref, A.postings, A.sess_ref, A.sess_items, A.idf, A.attr, A.rank_to_orig};
+  for (void* p : owned) ix->dev_allocs.push_back(p);
+  ix->device_bytes = A.n_items * 8 + A.item_hash_cap * sizeof(vmis::ItemHashEntry) + A.n_items * 8 + A.shard_entries * 4 +
+                     A.n_kept * 8 + A.sess_items_entries * 4 + A.n_items * 9 + A.n_kept * 4;
   return ix.release();
 }
 
@@ -276,6 +300,35 @@ vmis_index_t* vmis_index_from_sessions_sharded(const uint64_t* items, const uint
   return finish_index(std::move(ix), m, max_len, idf_weighting, device, shard, n_shards);
 }
 
+vmis_index_t* vmis_index_from_device_sessions(const uint64_t* d_items, const uint64_t* d_sess_off, const uint32_t* d_sess_ts,
+                                              size_t n_sessions, size_t m, size_t max_len, double idf_weighting, int device,
+                                              uint32_t shard, uint32_t n_shards) {
+  if (!d_items || !d_sess_off || !d_sess_ts) { fail(VMIS_ERR_ARG, "NULL device session arrays"); return nullptr; }
+  if (max_len == 0) { fail(VMIS_ERR_ARG, "the device build needs an explicit max_len"); return nullptr; }
+  std::unique_ptr<vmis_index> ix(new vmis_index());
+  if (select_device(device, &ix->sm_count) != VMIS_OK) return nullptr;
+  vmis::DeviceSessions s; s.items = d_items; s.off = d_sess_off; s.ts = d_sess_ts; s.n_sessions = n_sessions;
+  vmis::DeviceIndexArrays A; std::string err;
+  if (!vmis::build_index_device(s, m, max_len, idf_weighting, shard, n_shards, &A, &err)) { fail(VMIS_ERR_CUDA, "%s", err.c_str()); return nullptr; }
+  return adopt_device_index(std::move(ix), A, m, max_len, idf_weighting, device, shard, n_shards);
+}
+
+vmis_index_t* vmis_index_synth(uint64_t seed, uint64_t n_items, uint64_t n_sessions, size_t m, size_t max_len,
+                               double idf_weighting, int device, uint32_t shard, uint32_t n_shards) {
+  if (max_len == 0) max_len = 34;
+  std::unique_ptr<vmis_index> ix(new vmis_index());
+  if (select_device(device, &ix->sm_count) != VMIS_OK) return nullptr;
+  vmis::DeviceSessions s; std::string err;
+  if (!vmis::synth_sessions_device(seed, n_items, n_sessions, &s, &err)) { fail(VMIS_ERR_CUDA, "%s", err.c_str()); return nullptr; }
+  vmis::DeviceIndexArrays A;
+  const bool ok = vmis::build_index_device(s, m, max_len, idf_weighting, shard, n_shards, &A, &err);
+  cudaFree(const_cast<uint64_t*>(s.items)); cudaFree(const_cast<uint64_t*>(s.off)); cudaFree(const_cast<uint32_t*>(s.ts));
+  if (!ok) { fail(VMIS_ERR_CUDA, "%s", err.c_str()); return nullptr; }
+  vmis_index* r = adopt_device_index(std::move(ix), A, m, max_len, idf_weighting, device, shard, n_shards);
+  if (r) r->synth_interactions = s.n_entries;
+  return r;
+}
+
 int vmis_index_export_shard(const vmis_index_t* ix, void* handle64) {
   if (!ix || !handle64 || ix->device == VMIS_DEVICE_NONE) return fail(VMIS_ERR_ARG, "no device shard to export");
   static_assert(sizeof(cudaIpcMemHandle_t) == 64, "IPC handle size");
@@ -350,7 +403,7 @@ void vmis_index_free(vmis_index_t* ix) {
 
 int vmis_index_stats(const vmis_index_t* ix, vmis_stats_t* out) {
   if (!ix || !out) return fail(VMIS_ERR_ARG, "NULL argument");
-  out->n_sessions = ix->sessions.size();
+  out->n_sessions = ix->sessions.size() ? ix->sessions.size() : ix->n_sessions_kept;
   out->n_sessions_kept = ix->n_sessions_kept;
   out->n_items = ix->flat.item_key.size();
   out->n_pairs_kept = ix->flat.n_pairs_kept;
@@ -435,6 +488,7 @@ size_t vmis_postings(const vmis_index_t* ix, uint64_t item, uint32_t* out, size_
   if (!ix) return 0;
   const uint32_t d = vmis::host_lookup_item(ix->flat, item);
   if (d == vmis::kEmpty) return 0;
+  if (ix->flat.post_ref.empty()) { fail(VMIS_ERR_ARG, "postings live in HBM only"); return 0; }
   const uint2 ref = ix->flat.post_ref[d];
   if (ix->flat.postings.empty()) { fail(VMIS_ERR_ARG, "postings live in HBM only; use a VMIS_DEVICE_NONE handle to inspect them"); return ref.y; }
   const size_t base = ix->flat.shard_begin[d % ix->flat.n_shards] + (size_t)ref.x * 4;

@@ -51,6 +51,8 @@ def load_library():
         "vmis_index_from_csv_ex": (vp, [C.c_char_p, sz, f64, sz, i32]),
         "vmis_index_from_sessions": (vp, [_u64p, _u64p, _u32p, sz, sz, sz, f64, i32]),
         "vmis_index_from_sessions_sharded": (vp, [_u64p, _u64p, _u32p, sz, sz, sz, f64, i32, u32, u32]),
+        "vmis_index_from_device_sessions": (vp, [vp, vp, vp, sz, sz, sz, f64, i32, u32, u32]),
+        "vmis_index_synth": (vp, [u64, u64, u64, sz, sz, f64, i32, u32, u32]),
         "vmis_index_export_shard": (i32, [vp, vp]),
         "vmis_index_attach_shard": (i32, [vp, u32, vp]),
         "vmis_index_attach_shard_ptr": (i32, [vp, u32, vp]),
@@ -82,7 +84,8 @@ def load_library():
 
 EXPORTED_SYMBOLS = ("vmis_index_from_csv", "vmis_index_from_csv_ex", "vmis_index_from_sessions",
                     "vmis_index_from_sessions_sharded", "vmis_index_export_shard", "vmis_index_attach_shard",
-                    "vmis_index_attach_shard_ptr", "vmis_index_shard_ptr",
+                    "vmis_index_attach_shard_ptr", "vmis_index_shard_ptr", "vmis_index_from_device_sessions",
+                    "vmis_index_synth",
                     "vmis_index_set_attributes", "vmis_index_free", "vmis_index_stats", "vmis_predict_batch",
                     "vmis_predict_batch_device", "vmis_predict", "vmis_find_neighbors_batch", "vmis_items_for_session",
                     "vmis_idf", "vmis_find_attributes", "vmis_postings", "vmis_session_timestamp",
@@ -148,6 +151,23 @@ class VMISIndex:
         return cls(L.vmis_index_from_sessions_sharded(_p(items, C.c_uint64), _p(sess_off, C.c_uint64),
                                                       _p(sess_ts, C.c_uint32), len(sess_ts), m_most_recent_sessions,
                                                       max_len, float(idf_weighting), device, shard, n_shards))
+
+    @classmethod
+    def from_device_sessions(cls, d_items_ptr, d_off_ptr, d_ts_ptr, n_sessions, m_most_recent_sessions, max_len,
+                             idf_weighting, device=0, shard=0, n_shards=1):
+        """on-device prepare_hashmap over session arrays resident in HBM (raw device pointers)"""
+        L = load_library()
+        return cls(L.vmis_index_from_device_sessions(C.c_void_p(d_items_ptr), C.c_void_p(d_off_ptr), C.c_void_p(d_ts_ptr),
+                                                     n_sessions, m_most_recent_sessions, max_len, float(idf_weighting),
+                                                     device, shard, n_shards))
+
+    @classmethod
+    def synth(cls, seed, n_items, n_sessions, m_most_recent_sessions, max_len, idf_weighting, device=0, shard=0,
+              n_shards=1):
+        """synthetic workload generated and indexed entirely on the device (BASELINE configs 4-5)"""
+        L = load_library()
+        return cls(L.vmis_index_synth(seed, n_items, n_sessions, m_most_recent_sessions, max_len, float(idf_weighting),
+                                      device, shard, n_shards))
 
     def export_shard(self):
         buf = C.create_string_buffer(64)

@@ -1,0 +1,84 @@
+"""On-device index build (prepare_hashmap as radix sorts + kernels) and on-device synthetic generation:
+bit-identical to the host-built index and to the CPU oracle."""
+import numpy as np
+import pytest
+
+from util import csr, random_index_data
+
+pytestmark = pytest.mark.gpu
+
+
+def _dev(arr, torch):
+    view = {np.dtype(np.uint64): np.int64, np.dtype(np.uint32): np.int32}[arr.dtype]
+    return torch.from_numpy(np.ascontiguousarray(arr).view(view)).cuda()
+
+
+@pytest.mark.parametrize("seed", range(4))
+def test_device_build_matches_host_build_and_oracle(sb, oracle, seed):
+    torch = pytest.importorskip("torch")
+    rng = np.random.default_rng(seed)
+    items, off, ts = random_index_data(rng, int(rng.integers(200, 3000)), int(rng.integers(10, 300)),
+                                       max_len=int(rng.integers(3, 12)), unique_ts=bool(seed % 2),
+                                       id_scale=int(rng.integers(1, 1 << 30)))
+    m, max_len = int(rng.integers(1, 60)), int(rng.integers(3, 12))
+    d_items, d_off, d_ts = _dev(items, torch), _dev(off, torch), _dev(ts, torch)
+    dix = sb.VMISIndex.from_device_sessions(d_items.data_ptr(), d_off.data_ptr(), d_ts.data_ptr(), len(ts), m, max_len, 1.3)
+    hix = sb.VMISIndex.from_sessions(items, off, ts, m, max_len, 1.3, device=0)
+    oix = oracle.OracleIndex.from_sessions(items, off, ts, m, max_len, 1.3)
+    ds, hs = dix.stats(), hix.stats()
+    for key in ("n_sessions_kept", "n_items", "n_pairs_kept", "n_postings", "max_len", "m_build"):
+        assert ds[key] == hs[key], key
+    known = np.unique(items)
+    for it in known[::7]:
+        try:
+            want = hix.idf(int(it))
+        except KeyError:
+            with pytest.raises(KeyError):
+                dix.idf(int(it))
+            continue
+        assert dix.idf(int(it)) == want
+    queries = [[int(x) for x in rng.choice(known, size=int(rng.integers(1, 9)))] for _ in range(400)] + [[10 ** 15], []]
+    q_items, q_off = csr(queries)
+    for k, mq, n in [(20, m, 21), (500, 500, 40), (3, max(1, m // 2), 5)]:
+        a = sb.predict_batch(dix, queries, k, mq, n)
+        b = sb.predict_batch(hix, queries, k, mq, n)
+        o = oix.predict_batch(q_items, q_off, k, mq, n, mode=1)
+        for x, y, z in zip(a, b, o[:3]):
+            assert np.array_equal(x, y) and np.array_equal(x, z)
+        sa = dix.find_neighbors_batch(queries, k, mq)
+        sh = hix.find_neighbors_batch(queries, k, mq)
+        assert all(np.array_equal(x, y) for x, y in zip(sa, sh))
+    with pytest.raises(IndexError):
+        dix.items_for_session(0)            # no host mirror of the sessions on a device-built index
+
+
+def test_device_synth_matches_host_synth(sb, oracle):
+    n_items, n_sessions = 5000, 40000
+    six = sb.VMISIndex.synth(42, n_items, n_sessions, 1502, 34, 2.0)
+    items, off, ts = sb.synth_sessions(42, n_items, n_sessions)
+    hix = sb.VMISIndex.from_sessions(items, off, ts, 1502, 34, 2.0, device=0)
+    ss, hs = six.stats(), hix.stats()
+    for key in ("n_sessions_kept", "n_items", "n_pairs_kept", "n_postings"):
+        assert ss[key] == hs[key], key
+    q = sb.synth_queries(43, n_items, 2000, 4)
+    a = sb.predict_batch(six, q, 288, 1502, 21)
+    b = sb.predict_batch(hix, q, 288, 1502, 21)
+    assert all(np.array_equal(x, y) for x, y in zip(a, b))
+    oix = oracle.OracleIndex.from_sessions(items, off, ts, 1502, 34, 2.0)
+    o = oix.predict_batch(q[0], q[1], 288, 1502, 21, mode=1)
+    assert all(np.array_equal(x, y) for x, y in zip(a, o[:3]))
+
+
+def test_device_built_shards(sb):
+    n_items, n_sessions, n_shards = 4000, 30000, 4
+    full = sb.VMISIndex.synth(42, n_items, n_sessions, 300, 34, 2.0)
+    shards = [sb.VMISIndex.synth(42, n_items, n_sessions, 300, 34, 2.0, 0, s, n_shards) for s in range(n_shards)]
+    for a in range(n_shards):
+        for b in range(n_shards):
+            if a != b:
+                shards[a].attach_shard_ptr(b, shards[b].shard_ptr())
+    q = sb.synth_queries(43, n_items, 1500, 4)
+    want = sb.predict_batch(full, q, 100, 300, 21)
+    for sh in shards:
+        got = sb.predict_batch(sh, q, 100, 300, 21)
+        assert all(np.array_equal(x, y) for x, y in zip(got, want))
