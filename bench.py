@@ -279,7 +279,9 @@ def main():
     traffic = None
     tp = os.path.join(ROOT, "profiles", "traffic_bytes_per_launch.json")
     if os.path.exists(tp):
-        traffic = json.load(open(tp)).get("dram_bytes_per_launch")
+        tj = json.load(open(tp))
+        if tj.get("workload") == args.workload and tj.get("queries_per_launch") == args.batch:
+            traffic = tj.get("dram_bytes_per_launch")
     roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                 "traffic": traffic, "peak_source": peak_src, "kernel": "vmis_predict_kernel",
                 "algorithmic_bytes_per_query": timed_bytes / (args.steps * B)}
