@@ -246,3 +246,47 @@ def test_concurrent_host_threads(sb, toy):
     [t.start() for t in th]
     [t.join() for t in th]
     assert not errs, errs
+
+
+def test_batched_replay_evaluator_matches_readme(sb, toy, toy_dir):
+    """README.md:166-177 (evaluator on the toy data, example.toml: m=500, k=50, max_items=2, n=21):
+    931 evaluations, HitRate@20 0.6402, Mrr@20 0.3277 (tie order unpinned in the reference → ±0.004)."""
+    from serenade_b200.evaluate import evaluate, read_test_sessions as rts
+    gix, _, _ = toy
+    res = evaluate(gix, rts(os.path.join(toy_dir, "test.txt")), 50, 500, 21, 2, 20)
+    assert res["qty_evaluations"] == 931
+    assert res["hitrate"] == pytest.approx(0.6402, abs=0.0006)
+    assert res["mrr"] == pytest.approx(0.3277, abs=0.004)
+    res = evaluate(gix, rts(os.path.join(toy_dir, "test.txt")), 288, 1502, 21, 4, 20)   # README HPO optimum
+    assert res["mrr"] == pytest.approx(0.3401, abs=0.004) and res["hitrate"] > 0.65
+
+
+def test_full_size_properties_config3(sb, oracle):
+    """BASELINE config 3 at full size (60 M interactions / 1.76 M items, index generated and built on the device):
+    size-independent properties + oracle parity of a same-generator mid-size slice is covered elsewhere."""
+    gix = sb.VMISIndex.synth(42, 1_760_000, 11_556_000, 1502, 34, 2.0)
+    st = gix.stats()
+    assert st["n_pairs_kept"] == 60_017_474 and st["n_items"] == 1_721_361 and st["n_postings"] == 31_637_718
+    q_items, q_off = sb.synth_queries(43, 1_760_000, 1 << 15, 4)
+    n_q = len(q_off) - 1
+    ids, sc, cnt = sb.predict_batch(gix, (q_items, q_off), 288, 1502, 21)
+    # idempotence
+    ids2, sc2, cnt2 = sb.predict_batch(gix, (q_items, q_off), 288, 1502, 21)
+    assert np.array_equal(ids, ids2) and np.array_equal(sc, sc2) and np.array_equal(cnt, cnt2)
+    # permutation of the batch permutes the rows
+    perm = np.random.default_rng(0).permutation(n_q)
+    sessions = [q_items[q_off[i]:q_off[i + 1]] for i in range(n_q)]
+    p_ids, p_sc, p_cnt = sb.predict_batch(gix, [sessions[i] for i in perm], 288, 1502, 21)
+    assert np.array_equal(p_ids, ids[perm]) and np.array_equal(p_sc, sc[perm]) and np.array_equal(p_cnt, cnt[perm])
+    # order (score desc, id asc), no duplicates, current item never recommended, padding is zero
+    for q in range(0, n_q, 97):
+        c = cnt[q]
+        s, i = sc[q, :c], ids[q, :c]
+        assert (np.diff(s) <= 0).all()
+        ties = np.diff(s) == 0
+        assert (np.diff(i.astype(np.int64))[ties] > 0).all()
+        assert len(np.unique(i)) == c and sessions[q][-1] not in set(i.tolist())
+        assert (ids[q, c:] == 0).all() and (sc[q, c:] == 0).all()
+    # how_many prefix property: top-5 is the prefix of top-21; k/m monotone sanity on counts
+    ids5, sc5, cnt5 = sb.predict_batch(gix, (q_items, q_off), 288, 1502, 5)
+    assert np.array_equal(ids5, ids[:, :5] * (np.arange(5)[None, :] < cnt5[:, None]))
