@@ -226,48 +226,72 @@ int host_batch(const vmis_index* cix, const uint64_t* q_items, const uint32_t* q
       return fail(VMIS_ERR_LIMIT, "evolving session %u has %u items; kernel limit is %d", q, q_off[q + 1] - q_off[q], vmis::kMaxSessionLen);
   }
   CU_TRY(cudaSetDevice(ix->device));
-  std::unique_ptr<CallCtx> c;
-  rc = acquire_ctx(ix, &c);
-  if (rc) return rc;
-  cudaStream_t stream = stream_ ? static_cast<cudaStream_t>(stream_) : c->stream;
-  const size_t n_items = q_off[n_q];
+  // The batch is cut into chunks that flow through a small ring of call contexts (own stream, staging buffers and
+  // kernel workspace each): the H2D copy of chunk i+1 and the D2H copy of chunk i-1 overlap the kernel of chunk i.
+  // With a caller-provided stream everything is enqueued there, in order.
+  constexpr uint32_t kChunk = 1u << 17;
+  constexpr size_t kPipe = 3;
+  const uint32_t n_chunks = (n_q + kChunk - 1) / kChunk;
+  const size_t n_ctx = stream_ ? 1 : std::min<size_t>(kPipe, n_chunks);
   const size_t width = nb_mode ? k : how_many;
   auto al = [](size_t x) { return (x + 255) & ~size_t(255); };
-  const size_t o_items = 0, o_off = o_items + al(n_items * 8), o_ids = o_off + al((size_t(n_q) + 1) * 4);
-  const size_t o_sc = o_ids + al(size_t(n_q) * width * 8), o_cnt = o_sc + al(size_t(n_q) * width * 8);
-  const size_t total = o_cnt + al(size_t(n_q) * 4);
+  size_t max_items = 0;
+  for (uint32_t ch = 0; ch < n_chunks; ++ch) {
+    const uint32_t c0 = ch * kChunk, c1 = std::min(n_q, c0 + kChunk);
+    max_items = std::max<size_t>(max_items, q_off[c1] - q_off[c0]);
+  }
+  const uint32_t max_q = std::min(n_q, kChunk);
+  const size_t o_items = 0, o_off = o_items + al(max_items * 8), o_ids = o_off + al((size_t(max_q) + 1) * 4);
+  const size_t o_sc = o_ids + al(size_t(max_q) * width * 8), o_cnt = o_sc + al(size_t(max_q) * width * 8);
+  const size_t total = o_cnt + al(size_t(max_q) * 4);
+  std::vector<std::unique_ptr<CallCtx>> ring(n_ctx);
   auto body = [&]() -> int {
-    int r = ensure(&c->buf, &c->buf_cap, total);
-    if (r) return r;
-    unsigned char* b = static_cast<unsigned char*>(c->buf);
-    CU_TRY(cudaStreamWaitEvent(stream, c->done, 0));
-    if (n_items) CU_TRY(cudaMemcpyAsync(b + o_items, q_items, n_items * 8, cudaMemcpyHostToDevice, stream));
-    CU_TRY(cudaMemcpyAsync(b + o_off, q_off, (size_t(n_q) + 1) * 4, cudaMemcpyHostToDevice, stream));
-    vmis::PredictArgs a{};
-    a.q_items = reinterpret_cast<const uint64_t*>(b + o_items);
-    a.q_off = reinterpret_cast<const uint32_t*>(b + o_off);
-    a.n_q = n_q; a.k = k; a.m = m; a.how_many = how_many; a.biz = biz;
-    a.out_counts = reinterpret_cast<uint32_t*>(b + o_cnt);
-    if (nb_mode) { a.out_sess = reinterpret_cast<uint32_t*>(b + o_ids); a.out_sim = reinterpret_cast<double*>(b + o_sc); }
-    else { a.out_ids = reinterpret_cast<uint64_t*>(b + o_ids); a.out_scores = reinterpret_cast<double*>(b + o_sc); }
-    r = run_device(ix, c.get(), a, plan, stream);
-    if (r) return r;
-    if (nb_mode) {
-      if (k) {
-        CU_TRY(cudaMemcpyAsync(out_sess, b + o_ids, size_t(n_q) * k * 4, cudaMemcpyDeviceToHost, stream));
-        CU_TRY(cudaMemcpyAsync(out_sim, b + o_sc, size_t(n_q) * k * 8, cudaMemcpyDeviceToHost, stream));
-      }
-    } else if (how_many) {
-      CU_TRY(cudaMemcpyAsync(out_ids, b + o_ids, size_t(n_q) * how_many * 8, cudaMemcpyDeviceToHost, stream));
-      CU_TRY(cudaMemcpyAsync(out_scores, b + o_sc, size_t(n_q) * how_many * 8, cudaMemcpyDeviceToHost, stream));
+    for (auto& c : ring) {
+      int r = acquire_ctx(ix, &c);
+      if (r) return r;
+      r = ensure(&c->buf, &c->buf_cap, total);
+      if (r) return r;
     }
-    CU_TRY(cudaMemcpyAsync(out_counts, b + o_cnt, size_t(n_q) * 4, cudaMemcpyDeviceToHost, stream));
-    CU_TRY(cudaEventRecord(c->done, stream));
-    CU_TRY(cudaStreamSynchronize(stream));
+    for (uint32_t ch = 0; ch < n_chunks; ++ch) {
+      CallCtx* c = ring[ch % n_ctx].get();
+      cudaStream_t stream = stream_ ? static_cast<cudaStream_t>(stream_) : c->stream;
+      const uint32_t c0 = ch * kChunk, c1 = std::min(n_q, c0 + kChunk), nq = c1 - c0;
+      const size_t i0 = q_off[c0], ni = q_off[c1] - i0;
+      unsigned char* b = static_cast<unsigned char*>(c->buf);
+      CU_TRY(cudaStreamWaitEvent(stream, c->done, 0));
+      if (ni) CU_TRY(cudaMemcpyAsync(b + o_items, q_items + i0, ni * 8, cudaMemcpyHostToDevice, stream));
+      CU_TRY(cudaMemcpyAsync(b + o_off, q_off + c0, (size_t(nq) + 1) * 4, cudaMemcpyHostToDevice, stream));
+      vmis::PredictArgs a{};
+      a.q_items = reinterpret_cast<const uint64_t*>(b + o_items);
+      a.q_off = reinterpret_cast<const uint32_t*>(b + o_off);
+      a.q_item_base = (uint32_t)i0;
+      a.n_q = nq; a.k = k; a.m = m; a.how_many = how_many; a.biz = biz;
+      a.out_counts = reinterpret_cast<uint32_t*>(b + o_cnt);
+      if (nb_mode) { a.out_sess = reinterpret_cast<uint32_t*>(b + o_ids); a.out_sim = reinterpret_cast<double*>(b + o_sc); }
+      else { a.out_ids = reinterpret_cast<uint64_t*>(b + o_ids); a.out_scores = reinterpret_cast<double*>(b + o_sc); }
+      int r = run_device(ix, c, a, plan, stream);
+      if (r) return r;
+      if (nb_mode) {
+        if (k) {
+          CU_TRY(cudaMemcpyAsync(out_sess + size_t(c0) * k, b + o_ids, size_t(nq) * k * 4, cudaMemcpyDeviceToHost, stream));
+          CU_TRY(cudaMemcpyAsync(out_sim + size_t(c0) * k, b + o_sc, size_t(nq) * k * 8, cudaMemcpyDeviceToHost, stream));
+        }
+      } else if (how_many) {
+        CU_TRY(cudaMemcpyAsync(out_ids + size_t(c0) * how_many, b + o_ids, size_t(nq) * how_many * 8, cudaMemcpyDeviceToHost, stream));
+        CU_TRY(cudaMemcpyAsync(out_scores + size_t(c0) * how_many, b + o_sc, size_t(nq) * how_many * 8, cudaMemcpyDeviceToHost, stream));
+      }
+      CU_TRY(cudaMemcpyAsync(out_counts + c0, b + o_cnt, size_t(nq) * 4, cudaMemcpyDeviceToHost, stream));
+      CU_TRY(cudaEventRecord(c->done, stream));
+    }
+    for (auto& c : ring) {
+      cudaStream_t stream = stream_ ? static_cast<cudaStream_t>(stream_) : c->stream;
+      CU_TRY(cudaStreamSynchronize(stream));
+    }
     return VMIS_OK;
   };
   rc = body();
-  release_ctx(ix, std::move(c));
+  if (rc) cudaDeviceSynchronize();               // drain whatever was enqueued before the contexts go back to the pool
+  for (auto& c : ring) if (c) release_ctx(ix, std::move(c));
   return rc;
 }
 

@@ -518,16 +518,21 @@ vmis_predict_kernel(const IndexView ix, const PredictArgs a, const LaunchPlan pl
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
 
+  // thread 0 always has the NEXT work item in flight: the global atomic's round trip overlaps the current query
+  uint32_t next_q = 0;
+  if (tid == 0) next_q = atomicAdd(ws.counter, 1u);
   for (;;) {
     __syncthreads();
-    if (tid == 0) S.q = atomicAdd(ws.counter, 1u);
+    if (tid == 0) S.q = next_q;
     __syncthreads();
     const uint32_t q = S.q;
     if (q >= a.n_q) break;
+    if (tid == 0) next_q = atomicAdd(ws.counter, 1u);
 
     // ------------------------------------------------------------------ phase 0
-    const uint32_t qb = a.q_off[q];
-    const uint32_t Lfull = a.q_off[q + 1] - qb;
+    const uint32_t qo = a.q_off[q];
+    const uint32_t Lfull = a.q_off[q + 1] - qo;
+    const uint32_t qb = qo - a.q_item_base;
     const uint32_t L = Lfull > (uint32_t)kMaxSessionLen ? 0u : Lfull;   // over-long sessions are rejected host-side
     if (tid < (int)L) q_item[tid] = a.q_items[qb + (L - 1 - tid)];
     __syncthreads();

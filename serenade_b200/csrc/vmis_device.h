@@ -57,6 +57,7 @@ struct IndexView {
 struct PredictArgs {
   const uint64_t* q_items;    // device
   const uint32_t* q_off;      // device, n_q + 1
+  uint32_t q_item_base;       // q_off values are relative to q_items - q_item_base (chunks of a larger CSR batch)
   uint32_t n_q;
   uint32_t k, m, how_many;
   int biz;

@@ -290,3 +290,29 @@ def test_full_size_properties_config3(sb, oracle):
     # how_many prefix property: top-5 is the prefix of top-21; k/m monotone sanity on counts
     ids5, sc5, cnt5 = sb.predict_batch(gix, (q_items, q_off), 288, 1502, 5)
     assert np.array_equal(ids5, ids[:, :5] * (np.arange(5)[None, :] < cnt5[:, None]))
+
+
+def test_chunked_host_api_matches_device_api(sb):
+    """batches larger than one pipeline chunk (2^17) go through a ring of streams; rows must not move"""
+    torch = pytest.importorskip("torch")
+    gix = sb.VMISIndex.synth(42, 20_000, 60_000, 1502, 34, 2.0)
+    n_q, n = 300_001, 21
+    q_items, q_off = sb.synth_queries(43, 20_000, n_q, 4)
+    ids, sc, cnt = sb.predict_batch(gix, (q_items, q_off), 288, 1502, n)
+    dev = torch.device("cuda:0")
+    d_items = torch.from_numpy(q_items.view(np.int64)).to(dev)
+    d_off = torch.from_numpy(q_off.view(np.int32)).to(dev)
+    d_ids = torch.zeros((n_q, n), dtype=torch.int64, device=dev)
+    d_sc = torch.zeros((n_q, n), dtype=torch.float64, device=dev)
+    d_cnt = torch.zeros(n_q, dtype=torch.int32, device=dev)
+    lib = sb.load_library()
+    rc = lib.vmis_predict_batch_device(gix.handle, d_items.data_ptr(), d_off.data_ptr(), n_q, 288, 1502, n, 0,
+                                       d_ids.data_ptr(), d_sc.data_ptr(), d_cnt.data_ptr(), None, None)
+    assert rc == 0, lib.vmis_last_error()
+    torch.cuda.synchronize()
+    assert np.array_equal(d_cnt.cpu().numpy().view(np.uint32), cnt)
+    assert np.array_equal(d_ids.cpu().numpy().view(np.uint64), ids)
+    assert np.array_equal(d_sc.cpu().numpy(), sc)
+    sess, sim, ncnt = gix.find_neighbors_batch((q_items[:q_off[140_000]], q_off[:140_001]), 50, 1502)
+    s2, m2, c2 = gix.find_neighbors_batch((q_items[q_off[131_000]:q_off[140_000]], q_off[131_000:140_001] - q_off[131_000]), 50, 1502)
+    assert np.array_equal(sess[131_000:], s2) and np.array_equal(sim[131_000:], m2) and np.array_equal(ncnt[131_000:], c2)
