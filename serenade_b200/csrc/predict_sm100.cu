@@ -247,28 +247,31 @@ __device__ __forceinline__ uint32_t accumulate(const IndexView& ix, SmemLayout& 
     }
   };
   uint32_t wn = 0;                                   // warp-uniform count of claimed slots
-  uint32_t nxt_item = kEmpty; int32_t nxt_w = 0;
-  uint32_t base = warp * 32;
-  if (base < total) gather(base, nxt_item, nxt_w);
-  for (; base < total; base += kThreads) {
-    const uint32_t idx = nxt_item;
-    const int32_t w = nxt_w;
-    if (base + kThreads < total) gather(base + kThreads, nxt_item, nxt_w);
+  // A warp round covers 64 consecutive entries, two per lane: a lane that lands its first item early starts
+  // probing for its second one while slower lanes are still on their first, which shortens the converged loop.
+  uint32_t n0 = kEmpty, n1 = kEmpty; int32_t nw0 = 0, nw1 = 0;
+  uint32_t base = warp * 64;
+  if (base < total) { gather(base, n0, nw0); gather(base + 32, n1, nw1); }
+  for (; base < total; base += kThreads * 2) {
+    uint32_t idx = n0, pend = n1;
+    int32_t w = nw0, pw = nw1;
+    if (base + kThreads * 2 < total) { gather(base + kThreads * 2, n0, nw0); gather(base + kThreads * 2 + 32, n1, nw1); }
+    if (idx == kEmpty) { idx = pend; w = pw; pend = kEmpty; }
     bool done = idx == kEmpty;
     // double hashing: an odd stride visits every slot of the power-of-two table and avoids the primary
     // clustering of linear probing (shared memory has no locality to lose)
-    const uint32_t hv = idx * 0x9E3779B1u;
-    const uint32_t stride = ((hv >> 20) | 1u) & mask;
+    uint32_t hv = idx * 0x9E3779B1u;
+    uint32_t stride = ((hv >> 20) | 1u) & mask;
     uint32_t h = (hv >> 7) & mask;
     for (uint32_t steps = 0;; ++steps) {             // warp-converged: one probe step of every unfinished lane
-      bool claimed = false;
+      bool claimed = false, landed = false;
       if (!done) {
         uint32_t cur = *reinterpret_cast<volatile uint32_t*>(&keys[h]);
         if (cur == kEmpty) {
           cur = atomicCAS(&keys[h], kEmpty, idx);
           if (cur == kEmpty) { claimed = true; cur = idx; }
         }
-        if (cur == idx) { atomicAdd(&vals[h], w); done = true; }
+        if (cur == idx) { atomicAdd(&vals[h], w); landed = true; }
       }
       if (kRecord) {
         const uint32_t cm = __ballot_sync(kFull, claimed);
@@ -280,9 +283,14 @@ __device__ __forceinline__ uint32_t accumulate(const IndexView& ix, SmemLayout& 
           wn += (uint32_t)__popc(cm);
         }
       }
+      if (landed) {
+        if (pend != kEmpty) {
+          idx = pend; w = pw; pend = kEmpty;
+          hv = idx * 0x9E3779B1u; stride = ((hv >> 20) | 1u) & mask; h = (hv >> 7) & mask;
+        } else done = true;
+      } else if (!done) h = (h + stride) & mask;
       if (!__any_sync(kFull, !done)) break;
-      if (steps >= kMaxProbe) { S.overflow = 1u; break; }
-      if (!done) h = (h + stride) & mask;
+      if (steps >= 2 * kMaxProbe) { S.overflow = 1u; break; }
     }
   }
   return min(wn, seg_cap);
@@ -610,21 +618,25 @@ vmis_predict_kernel(const IndexView ix, const PredictArgs a, const LaunchPlan pl
             uint32_t ai = lo, bi = d0 - lo;
             uint64_t r[kVT];
             uint32_t vmask = 0;
+            // heads of both runs and the key of the last consumed A element stay in registers: one shared-memory
+            // load per merged element
+            uint64_t av = ai < na ? acc[ai] : 0ull;
+            uint32_t bk = bi < nb ? lst[bi] : 0u;
+            uint32_t pak = ai > 0 ? (uint32_t)(acc[ai - 1] >> 32) : kEmpty;   // kEmpty is never a session rank
 #pragma unroll
             for (int s = 0; s < kVT; ++s) {
               r[s] = 0;
               if (d0 + s < d1) {
-                const uint64_t av = ai < na ? acc[ai] : 0ull;
                 const uint32_t ak = (uint32_t)(av >> 32);
-                const uint32_t bk = bi < nb ? lst[bi] : 0u;
                 const bool takeA = (ai < na) && (bi >= nb || ak >= bk);
                 if (takeA) {
                   r[s] = av + ((bi < nb && bk == ak) ? cj : 0u);
-                  vmask |= 1u << s; ++ai;
+                  vmask |= 1u << s; pak = ak; ++ai;
+                  av = ai < na ? acc[ai] : 0ull;
                 } else {
-                  const bool dup = ai > 0 && (uint32_t)(acc[ai - 1] >> 32) == bk;
-                  if (!dup) { r[s] = ((uint64_t)bk << 32) | lowj; vmask |= 1u << s; }
+                  if (pak != bk) { r[s] = ((uint64_t)bk << 32) | lowj; vmask |= 1u << s; }
                   ++bi;
+                  bk = bi < nb ? lst[bi] : 0u;
                 }
               }
             }
