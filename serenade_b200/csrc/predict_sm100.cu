@@ -247,31 +247,28 @@ __device__ __forceinline__ uint32_t accumulate(const IndexView& ix, SmemLayout& 
     }
   };
   uint32_t wn = 0;                                   // warp-uniform count of claimed slots
-  // A warp round covers 64 consecutive entries, two per lane: a lane that lands its first item early starts
-  // probing for its second one while slower lanes are still on their first, which shortens the converged loop.
-  uint32_t n0 = kEmpty, n1 = kEmpty; int32_t nw0 = 0, nw1 = 0;
-  uint32_t base = warp * 64;
-  if (base < total) { gather(base, n0, nw0); gather(base + 32, n1, nw1); }
-  for (; base < total; base += kThreads * 2) {
-    uint32_t idx = n0, pend = n1;
-    int32_t w = nw0, pw = nw1;
-    if (base + kThreads * 2 < total) { gather(base + kThreads * 2, n0, nw0); gather(base + kThreads * 2 + 32, n1, nw1); }
-    if (idx == kEmpty) { idx = pend; w = pw; pend = kEmpty; }
+  uint32_t nxt_item = kEmpty; int32_t nxt_w = 0;
+  uint32_t base = warp * 32;
+  if (base < total) gather(base, nxt_item, nxt_w);
+  for (; base < total; base += kThreads) {
+    const uint32_t idx = nxt_item;
+    const int32_t w = nxt_w;
+    if (base + kThreads < total) gather(base + kThreads, nxt_item, nxt_w);
     bool done = idx == kEmpty;
     // double hashing: an odd stride visits every slot of the power-of-two table and avoids the primary
     // clustering of linear probing (shared memory has no locality to lose)
-    uint32_t hv = idx * 0x9E3779B1u;
-    uint32_t stride = ((hv >> 20) | 1u) & mask;
+    const uint32_t hv = idx * 0x9E3779B1u;
+    const uint32_t stride = ((hv >> 20) | 1u) & mask;
     uint32_t h = (hv >> 7) & mask;
     for (uint32_t steps = 0;; ++steps) {             // warp-converged: one probe step of every unfinished lane
-      bool claimed = false, landed = false;
+      bool claimed = false;
       if (!done) {
         uint32_t cur = *reinterpret_cast<volatile uint32_t*>(&keys[h]);
         if (cur == kEmpty) {
           cur = atomicCAS(&keys[h], kEmpty, idx);
           if (cur == kEmpty) { claimed = true; cur = idx; }
         }
-        if (cur == idx) { atomicAdd(&vals[h], w); landed = true; }
+        if (cur == idx) { atomicAdd(&vals[h], w); done = true; }
       }
       if (kRecord) {
         const uint32_t cm = __ballot_sync(kFull, claimed);
@@ -283,14 +280,9 @@ __device__ __forceinline__ uint32_t accumulate(const IndexView& ix, SmemLayout& 
           wn += (uint32_t)__popc(cm);
         }
       }
-      if (landed) {
-        if (pend != kEmpty) {
-          idx = pend; w = pw; pend = kEmpty;
-          hv = idx * 0x9E3779B1u; stride = ((hv >> 20) | 1u) & mask; h = (hv >> 7) & mask;
-        } else done = true;
-      } else if (!done) h = (h + stride) & mask;
       if (!__any_sync(kFull, !done)) break;
-      if (steps >= 2 * kMaxProbe) { S.overflow = 1u; break; }
+      if (steps >= kMaxProbe) { S.overflow = 1u; break; }
+      if (!done) h = (h + stride) & mask;
     }
   }
   return min(wn, seg_cap);
