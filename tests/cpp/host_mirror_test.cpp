@@ -1,0 +1,32 @@
+// CPU-side check of include/vmis.hpp on a host-only handle: the trait accessors behave like the reference's
+// (similarity_indexed.rs:8-24) and the query entry points fail loudly without a GPU.
+#include <cstdio>
+#include <cmath>
+#include "../../include/vmis.hpp"
+
+#define CHECK(c) do { if (!(c)) { std::printf("FAILED: %s (line %d)\n", #c, __LINE__); return 1; } } while (0)
+
+int main() {
+  // mod.rs:229-310 data
+  std::vector<std::vector<uint64_t>> sessions = {{920006, 920005, 920004}, {920005, 920004, 920003, 920002}};
+  auto index = vmis::VMISIndex::from_sessions(sessions, {1, 1}, 5, 5, 1.0, VMIS_DEVICE_NONE);
+  auto s0 = index.items_for_session(0);
+  CHECK(s0.second == 3 && s0.first[0] == 920006);
+  CHECK(std::fabs(index.idf(920005) - std::log(3.5)) < 1e-15);       // 7 pairs / df 2
+  CHECK(std::fabs(index.idf(920002) - std::log(7.0)) < 1e-15);
+  bool threw = false;
+  try { index.idf(42); } catch (const vmis::Error& e) { threw = e.code == VMIS_ERR_ARG; }
+  CHECK(threw);                                                        // the reference panics (vmis_index.rs:322)
+  auto a = index.find_attributes(920004);
+  CHECK(a && a->is_for_sale && !a->is_adult);                          // vmis_index.rs:514-517
+  CHECK(!index.find_attributes(42));
+  CHECK(index.stats().n_pairs_kept == 7 && index.stats().n_items == 5);
+  threw = false;
+  try { vmis::predict(index, {920005}, 500, 500, 20, false); } catch (const vmis::Error& e) { threw = e.code == VMIS_ERR_CUDA; }
+  CHECK(threw);                                                        // no CPU fallback
+  threw = false;
+  try { vmis::VMISIndex::new_from_csv("/nonexistent/train.txt", 500, 1.0, VMIS_DEVICE_NONE); } catch (const vmis::Error& e) { threw = e.code == VMIS_ERR_IO; }
+  CHECK(threw);
+  std::printf("host mirror ok\n");
+  return 0;
+}

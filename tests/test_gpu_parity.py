@@ -316,3 +316,21 @@ def test_chunked_host_api_matches_device_api(sb):
     sess, sim, ncnt = gix.find_neighbors_batch((q_items[:q_off[140_000]], q_off[:140_001]), 50, 1502)
     s2, m2, c2 = gix.find_neighbors_batch((q_items[q_off[131_000]:q_off[140_000]], q_off[131_000:140_001] - q_off[131_000]), 50, 1502)
     assert np.array_equal(sess[131_000:], s2) and np.array_equal(sim[131_000:], m2) and np.array_equal(ncnt[131_000:], c2)
+
+
+def test_cpp_evaluator_tool(toy_dir, tmp_path):
+    """tools/evaluator.cpp (the reference's evaluator binary over include/vmis.hpp): KAT + README run"""
+    import subprocess
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    exe = tmp_path / "evaluator"
+    subprocess.check_call(["g++", "-O2", "-std=c++17", "-o", str(exe), os.path.join(root, "tools", "evaluator.cpp"),
+                           "-L" + os.path.join(root, "serenade_b200"), "-lvmis_b200",
+                           "-Wl,-rpath," + os.path.join(root, "serenade_b200")])
+    out = subprocess.run([str(exe), "--kat"], capture_output=True, text=True)
+    assert out.returncode == 0 and "KAT ok: 4 recommendations, first 920004" in out.stdout, out.stdout + out.stderr
+    out = subprocess.run([str(exe), os.path.join(toy_dir, "train.txt"), os.path.join(toy_dir, "test.txt"), "500", "50", "21", "2", "1"],
+                         capture_output=True, text=True)
+    assert out.returncode == 0, out.stderr
+    assert "Qty test evaluations: 931" in out.stdout
+    mrr, hr = [float(x) for x in out.stdout.split("Mrr@20,HitRate@20\n")[1].split("\n")[0].split(",")]
+    assert hr == pytest.approx(0.6402, abs=0.0006) and mrr == pytest.approx(0.3277, abs=0.004)

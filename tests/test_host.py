@@ -182,3 +182,14 @@ def test_sharded_posting_layout_matches_unsharded(sb):
         sb.VMISIndex.from_sessions_sharded(items, off, ts, 25, 7, 1.0, sb.DEVICE_NONE, 2, 2)
     with pytest.raises(sb.VmisError):
         sb.VMISIndex.from_sessions_sharded(items, off, ts, 25, 7, 1.0, sb.DEVICE_NONE, 0, 9)
+
+
+def test_cpp_host_mirror(tmp_path):
+    """include/vmis.hpp (the C++ mirror of VMISIndex / predict) against a host-only handle"""
+    import subprocess
+    exe = tmp_path / "host_mirror_test"
+    subprocess.check_call(["g++", "-O1", "-std=c++17", "-o", str(exe), os.path.join(ROOT, "tests", "cpp", "host_mirror_test.cpp"),
+                           "-L" + os.path.join(ROOT, "serenade_b200"), "-lvmis_b200",
+                           "-Wl,-rpath," + os.path.join(ROOT, "serenade_b200")])
+    out = subprocess.run([str(exe)], capture_output=True, text=True)
+    assert out.returncode == 0 and "host mirror ok" in out.stdout, out.stdout + out.stderr
