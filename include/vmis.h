@@ -184,6 +184,18 @@ int vmis_synth_sessions(uint64_t seed, uint64_t n_items, uint64_t n_sessions, ui
 int vmis_synth_queries(uint64_t seed, uint64_t n_items, uint32_t n_q, uint32_t max_items_in_session,
                        uint64_t* q_items, uint32_t* q_off);
 
+/* ---- online call shape: micro-batching (recommend_resource.rs:56 called from actix workers, serving.rs:62-94) ----
+ * Worker threads call vmis_batcher_predict() with ONE evolving session each (the exact shape of mod.rs:118-125) and
+ * block; a dispatcher thread turns the waiting requests into one vmis_predict_batch call as soon as max_batch are
+ * queued or the oldest has waited max_wait_us.  Returns the number of recommendations (>= 0) or a negative error. */
+typedef struct vmis_batcher vmis_batcher_t;
+vmis_batcher_t* vmis_batcher_create(const vmis_index_t* index, uint32_t k, uint32_t m, uint32_t how_many,
+                                    int enable_business_logic, uint32_t max_batch, uint32_t max_wait_us);
+int vmis_batcher_predict(vmis_batcher_t* batcher, const uint64_t* evolving_session, size_t len, uint64_t* out_ids,
+                         double* out_scores);
+int vmis_batcher_stats(vmis_batcher_t* batcher, uint64_t* n_batches, uint64_t* n_requests);
+void vmis_batcher_destroy(vmis_batcher_t* batcher);
+
 /* ---- misc ---------------------------------------------------------------- */
 
 const char* vmis_last_error(void);   /* message of the last failure on this thread */

@@ -71,6 +71,10 @@ def load_library():
         "vmis_session_timestamp": (i32, [vp, u32, _u32p]),
         "vmis_synth_sessions": (i32, [u64, u64, u64, _u64p, _u64p, _u32p, _u64p]),
         "vmis_synth_queries": (i32, [u64, u64, u32, u32, _u64p, _u32p]),
+        "vmis_batcher_create": (vp, [vp, u32, u32, u32, i32, u32, u32]),
+        "vmis_batcher_predict": (i32, [vp, _u64p, sz, _u64p, _f64p]),
+        "vmis_batcher_stats": (i32, [vp, _u64p, _u64p]),
+        "vmis_batcher_destroy": (None, [vp]),
         "vmis_last_error": (C.c_char_p, []),
         "vmis_last_error_code": (i32, []),
         "vmis_version": (C.c_char_p, []),
@@ -89,7 +93,8 @@ EXPORTED_SYMBOLS = ("vmis_index_from_csv", "vmis_index_from_csv_ex", "vmis_index
                     "vmis_index_set_attributes", "vmis_index_free", "vmis_index_stats", "vmis_predict_batch",
                     "vmis_predict_batch_device", "vmis_predict", "vmis_find_neighbors_batch", "vmis_items_for_session",
                     "vmis_idf", "vmis_find_attributes", "vmis_postings", "vmis_session_timestamp",
-                    "vmis_synth_sessions", "vmis_synth_queries", "vmis_last_error", "vmis_last_error_code",
+                    "vmis_synth_sessions", "vmis_synth_queries", "vmis_batcher_create", "vmis_batcher_predict",
+                    "vmis_batcher_stats", "vmis_batcher_destroy", "vmis_last_error", "vmis_last_error_code",
                     "vmis_version")
 
 
@@ -311,3 +316,36 @@ def synth_queries(seed, n_items, n_q, max_items_in_session=4):
     _check(L.vmis_synth_queries(seed, n_items, n_q, max_items_in_session, _p(q_items, C.c_uint64),
                                 _p(q_off, C.c_uint32)))
     return q_items[:q_off[-1]].copy(), q_off
+
+
+class Batcher:
+    """Micro-batching front for the online call shape (one evolving session per caller thread, as actix workers
+    call predict at recommend_resource.rs:56)."""
+
+    def __init__(self, index, k, m, how_many, enable_business_logic=False, max_batch=4096, max_wait_us=200):
+        self._index = index                       # keep the index alive
+        self._how_many = how_many
+        self._b = C.c_void_p(load_library().vmis_batcher_create(index.handle, k, m, how_many, int(enable_business_logic),
+                                                               max_batch, max_wait_us))
+        if not self._b:
+            raise VmisError(-1, "vmis_batcher_create failed")
+
+    def predict(self, evolving_session):
+        ev = np.ascontiguousarray(evolving_session, dtype=np.uint64)
+        ids = np.zeros(max(self._how_many, 1), dtype=np.uint64)
+        sc = np.zeros(max(self._how_many, 1), dtype=np.float64)
+        n = _check(load_library().vmis_batcher_predict(self._b, _p(ev, C.c_uint64), len(ev), _p(ids, C.c_uint64),
+                                                       _p(sc, C.c_double)))
+        return [(int(ids[i]), float(sc[i])) for i in range(n)]
+
+    def stats(self):
+        a, b = C.c_uint64(), C.c_uint64()
+        _check(load_library().vmis_batcher_stats(self._b, C.byref(a), C.byref(b)))
+        return {"batches": a.value, "requests": b.value}
+
+    def close(self):
+        if getattr(self, "_b", None) and _lib is not None:
+            _lib.vmis_batcher_destroy(self._b)
+        self._b = None
+
+    __del__ = close

@@ -334,3 +334,31 @@ def test_cpp_evaluator_tool(toy_dir, tmp_path):
     assert "Qty test evaluations: 931" in out.stdout
     mrr, hr = [float(x) for x in out.stdout.split("Mrr@20,HitRate@20\n")[1].split("\n")[0].split(",")]
     assert hr == pytest.approx(0.6402, abs=0.0006) and mrr == pytest.approx(0.3277, abs=0.004)
+
+
+def test_micro_batcher_online_shape(sb, toy):
+    """one evolving session per caller thread (actix workers, recommend_resource.rs:56) through the micro-batcher"""
+    import threading
+    gix, oix, tests = toy
+    queries, _ = evaluator_queries(tests, 4)
+    want = sb.predict_batch(gix, queries, 288, 1502, 21)
+    b = sb.Batcher(gix, 288, 1502, 21, False, max_batch=256, max_wait_us=500)
+    errs = []
+
+    def work(t):
+        try:
+            for q in range(t, len(queries), 16):
+                got = b.predict(queries[q])
+                c = want[2][q]
+                assert [g[0] for g in got] == want[0][q, :c].tolist() and [g[1] for g in got] == want[1][q, :c].tolist()
+        except Exception as e:  # noqa: BLE001
+            errs.append(e)
+
+    th = [threading.Thread(target=work, args=(t,)) for t in range(16)]
+    [x.start() for x in th]
+    [x.join() for x in th]
+    assert not errs, errs[:2]
+    st = b.stats()
+    assert st["requests"] == len(queries) and st["batches"] < len(queries)      # requests really were coalesced
+    assert b.predict([]) == []
+    b.close()
