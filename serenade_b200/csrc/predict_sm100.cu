@@ -181,10 +181,10 @@ union Scratch {
   struct { uint32_t top32[kWarps * 32]; uint32_t queue[kWarps][64]; } sel;
 };
 
-// bytes of the neighbour arrays (3 x K + 1 words), never smaller than the scratch that aliases them
+// bytes of the neighbour arrays (4 x K + 1 words), never smaller than the scratch that aliases them
 __host__ __device__ constexpr size_t nbr_bytes_min() { return sizeof(Scratch); }
 __host__ __device__ inline size_t nbr_bytes(uint32_t k) {
-  size_t b = (size_t(k) * 3 + 1) * 4;
+  size_t b = (size_t(k) * 4 + 1) * 4;
   if (b < nbr_bytes_min()) b = nbr_bytes_min();
   return (b + 15) & ~size_t(15);
 }
@@ -220,8 +220,7 @@ __device__ __forceinline__ int32_t session_weight10(uint32_t low) {
 struct FlatMap {
   const uint32_t* bits;     // [words] bit b of word w: entry 32w+b starts a neighbour's list
   const uint16_t* dir;      // [words] neighbour owning entry 32w
-  const uint32_t* start;    // [nn+1]  first flat entry of each neighbour
-  const uint32_t* off4;     // [nn]    item list offset / 4
+  const uint64_t* delta;    // [nn]    (item list offset in sess_items) - (first flat entry): item of entry e = sess_items[delta + e]
   const uint32_t* w;        // [nn]    weight 10*linear_score*numerator
 };
 
@@ -241,7 +240,7 @@ __device__ __forceinline__ uint32_t accumulate(const IndexView& ix, SmemLayout& 
     if (e < total) {
       const uint32_t word = base >> 5, b = fm.bits[word];
       const uint32_t i = (uint32_t)fm.dir[word] + (uint32_t)__popc(b & le_mask) - (b & 1u);
-      item = __ldg(ix.sess_items + (size_t)fm.off4[i] * 4 + (e - fm.start[i]));
+      item = __ldg(ix.sess_items + (fm.delta[i] + e));
       wgt = (int32_t)fm.w[i];
       if (item == last_idx) item = kEmpty;
     }
@@ -260,8 +259,8 @@ __device__ __forceinline__ uint32_t accumulate(const IndexView& ix, SmemLayout& 
     const uint32_t hv = idx * 0x9E3779B1u;
     const uint32_t stride = ((hv >> 20) | 1u) & mask;
     uint32_t h = (hv >> 7) & mask;
+    bool claimed = false;                            // a lane claims at most one slot per round (its item's)
     for (uint32_t steps = 0;; ++steps) {             // warp-converged: one probe step of every unfinished lane
-      bool claimed = false;
       if (!done) {
         uint32_t cur = *reinterpret_cast<volatile uint32_t*>(&keys[h]);
         if (cur == kEmpty) {
@@ -270,19 +269,17 @@ __device__ __forceinline__ uint32_t accumulate(const IndexView& ix, SmemLayout& 
         }
         if (cur == idx) { atomicAdd(&vals[h], w); done = true; }
       }
-      if (kRecord) {
-        const uint32_t cm = __ballot_sync(kFull, claimed);
-        if (cm) {
-          if (claimed) {
-            const uint32_t n = wn + (uint32_t)__popc(cm & lt_mask);
-            if (n < seg_cap) occ_seg[n] = (uint16_t)h; else S.overflow = 1u;
-          }
-          wn += (uint32_t)__popc(cm);
-        }
-      }
       if (!__any_sync(kFull, !done)) break;
       if (steps >= kMaxProbe) { S.overflow = 1u; break; }
       if (!done) h = (h + stride) & mask;
+    }
+    if (kRecord) {                                   // h still addresses the slot the lane landed on
+      const uint32_t cm = __ballot_sync(kFull, claimed);
+      if (claimed) {
+        const uint32_t n = wn + (uint32_t)__popc(cm & lt_mask);
+        if (n < seg_cap) occ_seg[n] = (uint16_t)h; else S.overflow = 1u;
+      }
+      wn += (uint32_t)__popc(cm);
     }
   }
   return min(wn, seg_cap);
@@ -486,10 +483,10 @@ vmis_predict_kernel(const IndexView ix, const PredictArgs a, const LaunchPlan pl
   unsigned char* dyn = smem_raw + ((sizeof(SmemLayout) + 15) & ~size_t(15));
   // neighbour arrays
   Scratch& X = *reinterpret_cast<Scratch*>(dyn);
-  uint32_t* nbr_sid = reinterpret_cast<uint32_t*>(dyn);            // [K+1] time rank of the neighbour session ...
-  uint32_t* nbr_start = nbr_sid;                                   //       ... later its first flat item entry
+  uint64_t* nbr_delta = reinterpret_cast<uint64_t*>(dyn);          // [K]   item list offset - first flat entry (phase 2)
+  uint32_t* nbr_sid = reinterpret_cast<uint32_t*>(nbr_delta + a.k);// [K+1] time rank of the neighbour session ...
+  uint32_t* nbr_start = nbr_sid;                                   //       ... later its item list length
   uint32_t* nbr_low = nbr_sid + a.k + 1;                           // [K]   pos|numerator, later the weight w
-  uint32_t* nbr_off4 = nbr_low + a.k;                              // [K]   item list offset / 4
   unsigned char* region = dyn + nbr_bytes(a.k);
   // phase-0 view of the region
   uint64_t* q_item = reinterpret_cast<uint64_t*>(region);          // evolving session reversed: [pos]
@@ -765,7 +762,7 @@ vmis_predict_kernel(const IndexView ix, const PredictArgs a, const LaunchPlan pl
     int my_len = 0;
     for (uint32_t i = i0; i < i1; ++i) {
       const uint2 r = ix.sess_ref[nbr_sid[i]];
-      nbr_off4[i] = r.x; nbr_start[i] = r.y; my_len += (int)r.y;    // length parked until the scan
+      nbr_delta[i] = (uint64_t)r.x * 4; nbr_start[i] = r.y; my_len += (int)r.y;    // offset and length parked until the scan
       uint32_t low = nbr_low[i];
       if (!pos_from_lists) {                                        // reference scan (mod.rs:133-138)
         const uint32_t* items = ix.sess_items + (size_t)r.x * 4;
@@ -783,12 +780,11 @@ vmis_predict_kernel(const IndexView ix, const PredictArgs a, const LaunchPlan pl
     const uint32_t total_items = (uint32_t)total_i;
     for (uint32_t i = i0; i < i1; ++i) {
       const uint32_t len = nbr_start[i], last = run + len - 1;
-      nbr_start[i] = run;
+      nbr_delta[i] -= run;
       atomicOr(&fbits[run >> 5], 1u << (run & 31u));
       for (uint32_t wd = (run + 31u) >> 5; wd <= (last >> 5); ++wd) fdir[wd] = (uint16_t)i;
       run += len;
     }
-    if (tid == 0) nbr_start[nn] = total_items;
     __syncthreads();
 
     // ------------------------------------------------------------------ phase 2b + 3
@@ -798,7 +794,7 @@ vmis_predict_kernel(const IndexView ix, const PredictArgs a, const LaunchPlan pl
     // shared-memory score table first; the rare query whose neighbours hold more distinct items than its
     // occupancy budget is redone on this CTA's global table
     FlatMap fm;
-    fm.bits = fbits; fm.dir = fdir; fm.start = nbr_start; fm.off4 = nbr_off4; fm.w = nbr_low;
+    fm.bits = fbits; fm.dir = fdir; fm.delta = nbr_delta; fm.w = nbr_low;
     // every warp records the slots it claims in its own segment of the list and scores exactly those in phase 3
     const uint32_t seg = plan.occ_cap / kWarps;
     if (nn == 0 || N == 0) {
