@@ -224,15 +224,6 @@ struct FlatMap {
   const uint32_t* w;        // [nn]    weight 10*linear_score*numerator
 };
 
-// volatile 16-byte load of one table bucket (shared table when kShared, else the global overflow table)
-template <bool kShared>
-__device__ __forceinline__ uint4 ld_bucket(const uint32_t* p) {
-  uint4 r;
-  if (kShared) asm volatile("ld.volatile.shared.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w) : "r"(smem_u32(p)));
-  else asm volatile("ld.volatile.global.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w) : "l"(p));
-  return r;
-}
-
 constexpr uint32_t kMaxProbe = 512;        // a probe sequence this long means the table is (nearly) full
 
 // Returns the number of slots this WARP claimed; when kRecord, their indices are appended to the warp's own
@@ -263,36 +254,24 @@ __device__ __forceinline__ uint32_t accumulate(const IndexView& ix, SmemLayout& 
     const int32_t w = nxt_w;
     if (base + kThreads < total) gather(base + kThreads, nxt_item, nxt_w);
     bool done = idx == kEmpty;
-    // Bucketized double hashing: the table is probed in aligned buckets of 4 slots (one 16-byte shared load); an
-    // item lives in the first bucket of its probe sequence that had a free slot when it arrived, at the first free
-    // position.  A probe step fails only when all 4 slots hold other items (~load^4), so the converged loop rarely
-    // needs more than two steps; the odd bucket stride visits every bucket of the power-of-two table.
+    // double hashing: an odd stride visits every slot of the power-of-two table and avoids the primary
+    // clustering of linear probing (shared memory has no locality to lose)
     const uint32_t hv = idx * 0x9E3779B1u;
-    const uint32_t bmask = mask >> 2;                                       // bucket index mask
-    const uint32_t bstride = ((hv >> 20) | 1u) & bmask;
-    uint32_t hb = (hv >> 7) & bmask;
-    uint32_t h = 0;                                                         // slot the lane finally landed on
+    const uint32_t stride = ((hv >> 20) | 1u) & mask;
+    uint32_t h = (hv >> 7) & mask;
     bool claimed = false;                            // a lane claims at most one slot per round (its item's)
     for (uint32_t steps = 0;; ++steps) {             // warp-converged: one probe step of every unfinished lane
       if (!done) {
-        const uint32_t s0 = hb << 2;
-        const uint4 kk = ld_bucket<kRecord>(&keys[s0]);
-        int pos = kk.x == idx ? 0 : kk.y == idx ? 1 : kk.z == idx ? 2 : kk.w == idx ? 3 : -1;
-        bool stay = false;
-        if (pos < 0) {
-          const int e = kk.x == kEmpty ? 0 : kk.y == kEmpty ? 1 : kk.z == kEmpty ? 2 : kk.w == kEmpty ? 3 : -1;
-          if (e >= 0) {
-            const uint32_t old = atomicCAS(&keys[s0 + e], kEmpty, idx);
-            if (old == kEmpty) { claimed = true; pos = e; }
-            else if (old == idx) pos = e;
-            else stay = true;                        // lost the slot to another item: look at this bucket again
-          }
+        uint32_t cur = *reinterpret_cast<volatile uint32_t*>(&keys[h]);
+        if (cur == kEmpty) {
+          cur = atomicCAS(&keys[h], kEmpty, idx);
+          if (cur == kEmpty) { claimed = true; cur = idx; }
         }
-        if (pos >= 0) { h = s0 + (uint32_t)pos; atomicAdd(&vals[h], w); done = true; }
-        else if (!stay) hb = (hb + bstride) & bmask;
+        if (cur == idx) { atomicAdd(&vals[h], w); done = true; }
       }
       if (!__any_sync(kFull, !done)) break;
       if (steps >= kMaxProbe) { S.overflow = 1u; break; }
+      if (!done) h = (h + stride) & mask;
     }
     if (kRecord) {                                   // h still addresses the slot the lane landed on
       const uint32_t cm = __ballot_sync(kFull, claimed);
