@@ -1,25 +1,31 @@
 // serenade_b200/csrc/predict_sm100.cu — the VMIS-kNN predict_next kernel for sm_100a.
 //
-// One persistent CTA per SM slot pulls evolving sessions from a global work
-// counter and runs the whole query in shared memory:
+// Persistent CTAs (5 per SM, 256 threads, ~44 KB shared memory) pull evolving sessions from a global work
+// counter (the next index is always prefetched) and run one query each, end to end in shared memory:
 //
-//   phase 0  de-duplicate the evolving session (vmis_index.rs:335-348), translate
-//            external item ids through the HBM item hash
-//   phase 1  m-sample: fold the time-descending posting lists of the distinct items
-//            with a block-wide merge-path merge that de-duplicates, sums the integer
-//            similarity numerators and truncates to the m most recent sessions
+//   phase 0  de-duplicate the evolving session (vmis_index.rs:335-348), translate external item ids
+//            through the HBM item hash; one packed block scan orders the distinct known items
+//   phase 1  m-sample: the time-descending posting lists of the distinct items (local HBM, or a peer
+//            GPU's HBM over NVLink when the index is item-sharded) are streamed into shared memory by
+//            TMA bulk copies (cp.async.bulk + mbarrier, double buffered) and folded one by one with a
+//            block-wide merge-path merge that de-duplicates, sums the integer similarity numerators,
+//            keeps the first-match position and truncates to the m most recent sessions
 //            (closed form of the heap procedure of vmis_index.rs:344-391)
-//   phase 1b top-k neighbours by (numerator desc, recency desc) — threshold search
-//            + ordered prefix scan (vmis_index.rs:394-412)
-//   phase 2  per neighbour: first-match position → linear session weight
-//            (mod.rs:133-142, :110-116); integer score numerators are accumulated
-//            per item in a shared-memory hash table (mod.rs:144-153)
-//   phase 3  drop the current item (mod.rs:157-160), business rules (:162-182),
-//            f64 score = g(idf)·A/(10·u), warp-bitonic top-n (mod.rs:185-214)
+//   phase 1b top-k neighbours by (numerator desc, recency desc): packed / ballot histogram or binary
+//            search for the threshold numerator, one ordered scan for the ties (vmis_index.rs:394-412)
+//   phase 2a neighbour directory: item-list refs, integer weight 10·linear_score·numerator
+//            (mod.rs:133-142, :110-116), flat entry → neighbour map (bitmap + word directory)
+//   phase 2b A[item] += weight for every item of every neighbour (mod.rs:144-153): one item per lane,
+//            warp-converged double-hashing inserts into a 4096-slot shared table; every warp keeps the
+//            list of slots it claimed; rare overflow → the CTA's global table
+//   phase 3  drop the current item (mod.rs:157-160), business rules (:162-182), top-n by (score desc,
+//            item id asc) (mod.rs:185-214): fp32 coarse keys through a u32 warp-bitonic network with a
+//            shared lower bound, the 32 survivors rescored exactly (f64 g(idf)·A/(10·u)) and sorted once;
+//            a margin test proves the survivors contain the exact top-n, else an exact 96-bit network runs
 //
-// All item/session arithmetic is integer and order independent; the only floating
-// point is one f64 multiply + divide per candidate item, so results are bit-exact
-// against oracle/vmis_oracle.cpp canonical mode.
+// All session/item arithmetic is integer and order independent; the only floating point that reaches the
+// output is one f64 multiply + divide per final candidate, so results are bit-exact against the canonical mode
+// of the CPU checker whatever the thread scheduling, batch order or index sharding.
 #include "vmis_device.h"
 
 #include <algorithm>
@@ -541,13 +547,16 @@ vmis_predict_kernel(const IndexView ix, const PredictArgs a, const LaunchPlan pl
       for (int t = 0; t < tid; ++t) if (q_item[t] == it) { distinct = false; break; }
       if (distinct) my_idx = lookup_item(ix, it);
     }
-    const uint32_t u = (uint32_t)__syncthreads_count(distinct);          // unique items incl. unknown (:335-339)
-    // compact distinct known items in position order
+    // one packed scan: low half compacts the distinct KNOWN items in position order, high half counts the
+    // unique items including unknown ones (vmis_index.rs:335-339)
+    uint32_t u;
     {
-      int flag = (my_idx != kEmpty) ? 1 : 0, total;
-      int pos = block_excl_scan(flag, S.scan, par, total);
-      if (flag) { S.d_idx[pos] = my_idx; S.d_pos[pos] = (uint32_t)tid; }
-      if (tid == 0) S.nd = (uint32_t)total;
+      const int flag = (my_idx != kEmpty) ? 1 : 0;
+      int total;
+      const int pos = block_excl_scan(flag | ((distinct ? 1 : 0) << 16), S.scan, par, total) & 0xFFFF;
+      if (flag) { S.d_idx[pos] = my_idx; S.d_pos[pos] = (uint8_t)tid; }
+      if (tid == 0) S.nd = (uint32_t)total & 0xFFFFu;
+      u = (uint32_t)total >> 16;
     }
     __syncthreads();
     const uint32_t nd = S.nd;
