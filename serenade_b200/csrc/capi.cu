@@ -7,6 +7,7 @@
 #include <algorithm>
 #include <cstdarg>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <memory>
 #include <mutex>
@@ -95,11 +96,41 @@ int select_device(int device, int* sm_count) {
   return VMIS_OK;
 }
 
+vmis_index* adopt_device_index(std::unique_ptr<vmis_index> ix, vmis::DeviceIndexArrays& A, size_t m, size_t max_len,
+                               double idf_w, int device, uint32_t shard, uint32_t n_shards);
+
+// Sessions held on the host → index.  With a device the build itself runs there (build_sm100.cu: ~0.1 s for 60 M
+// interactions instead of ~10 s on one host core; the reference rebuilds the index for every HPO trial,
+// objective.rs:17); the host builder serves VMIS_DEVICE_NONE handles, max_len > 128 and VMIS_BUILD=host.
 vmis_index* finish_index(std::unique_ptr<vmis_index> ix, size_t m, size_t max_len, double idf_w, int device,
                          uint32_t shard = 0, uint32_t n_shards = 1) {
   std::string err;
   if (n_shards == 0 || shard >= n_shards) { fail(VMIS_ERR_ARG, "shard %u out of range [0,%u)", shard, n_shards); return nullptr; }
   if (max_len == 0) max_len = vmis::session_length_p99_5(ix->sessions);
+  const char* how = std::getenv("VMIS_BUILD");
+  if (device != VMIS_DEVICE_NONE && max_len <= 128 && m >= 1 && !(how && !std::strcmp(how, "host")) && ix->sessions.size() > 0) {
+    if (select_device(device, &ix->sm_count) != VMIS_OK) return nullptr;
+    const vmis::Sessions& S = ix->sessions;
+    void *d_items = nullptr, *d_off = nullptr, *d_ts = nullptr;
+    bool ok = cudaMalloc(&d_items, std::max<size_t>(S.items.size() * 8, 16)) == cudaSuccess &&
+              cudaMalloc(&d_off, S.off.size() * 8) == cudaSuccess && cudaMalloc(&d_ts, std::max<size_t>(S.ts.size() * 4, 16)) == cudaSuccess &&
+              cudaMemcpy(d_items, S.items.data(), S.items.size() * 8, cudaMemcpyHostToDevice) == cudaSuccess &&
+              cudaMemcpy(d_off, S.off.data(), S.off.size() * 8, cudaMemcpyHostToDevice) == cudaSuccess &&
+              cudaMemcpy(d_ts, S.ts.data(), S.ts.size() * 4, cudaMemcpyHostToDevice) == cudaSuccess;
+    vmis::DeviceIndexArrays A;
+    if (ok) {
+      vmis::DeviceSessions ds; ds.items = (const uint64_t*)d_items; ds.off = (const uint64_t*)d_off; ds.ts = (const uint32_t*)d_ts;
+      ds.n_sessions = S.size(); ds.n_entries = S.items.size();
+      ok = vmis::build_index_device(ds, m, max_len, idf_w, shard, n_shards, &A, &err);
+    } else err = cudaGetErrorString(cudaGetLastError());
+    cudaFree(d_items); cudaFree(d_off); cudaFree(d_ts);
+    if (ok) return adopt_device_index(std::move(ix), A, m, max_len, idf_w, device, shard, n_shards);
+    if (err.find("duplicate item") != std::string::npos || err.find("no training session") != std::string::npos) {
+      fail(VMIS_ERR_ARG, "%s", err.c_str());
+      return nullptr;
+    }
+    cudaGetLastError();   // e.g. out of memory during the sorts: fall through to the host builder
+  }
   if (!vmis::build_flat_index(ix->sessions, m, max_len, idf_w, n_shards, &ix->flat, &err)) { fail(VMIS_ERR_ARG, "%s", err.c_str()); return nullptr; }
   ix->shard = shard;
   ix->n_sessions_kept = ix->flat.rank_to_orig.size();
@@ -134,7 +165,7 @@ vmis_index* finish_index(std::unique_ptr<vmis_index> ix, size_t m, size_t max_le
   return ix.release();
 }
 
-// wrap the arrays of an on-device build into a handle
+// wrap the arrays of an on-device build into a handle (ix->sessions, if any, stays as the host mirror)
 vmis_index* adopt_device_index(std::unique_ptr<vmis_index> ix, vmis::DeviceIndexArrays& A, size_t m, size_t max_len,
                                double idf_w, int device, uint32_t shard, uint32_t n_shards) {
   vmis::FlatIndex& F = ix->flat;

@@ -1,5 +1,7 @@
 """On-device index build (prepare_hashmap as radix sorts + kernels) and on-device synthetic generation:
 bit-identical to the host-built index and to the CPU oracle."""
+import os
+
 import numpy as np
 import pytest
 
@@ -23,7 +25,11 @@ def test_device_build_matches_host_build_and_oracle(sb, oracle, seed):
     m, max_len = int(rng.integers(1, 60)), int(rng.integers(3, 12))
     d_items, d_off, d_ts = _dev(items, torch), _dev(off, torch), _dev(ts, torch)
     dix = sb.VMISIndex.from_device_sessions(d_items.data_ptr(), d_off.data_ptr(), d_ts.data_ptr(), len(ts), m, max_len, 1.3)
-    hix = sb.VMISIndex.from_sessions(items, off, ts, m, max_len, 1.3, device=0)
+    os.environ["VMIS_BUILD"] = "host"                    # force the host CSR builder for the comparison
+    try:
+        hix = sb.VMISIndex.from_sessions(items, off, ts, m, max_len, 1.3, device=0)
+    finally:
+        del os.environ["VMIS_BUILD"]
     oix = oracle.OracleIndex.from_sessions(items, off, ts, m, max_len, 1.3)
     ds, hs = dix.stats(), hix.stats()
     for key in ("n_sessions_kept", "n_items", "n_pairs_kept", "n_postings", "max_len", "m_build"):
@@ -49,14 +55,23 @@ def test_device_build_matches_host_build_and_oracle(sb, oracle, seed):
         sh = hix.find_neighbors_batch(queries, k, mq)
         assert all(np.array_equal(x, y) for x, y in zip(sa, sh))
     with pytest.raises(IndexError):
-        dix.items_for_session(0)            # no host mirror of the sessions on a device-built index
+        dix.items_for_session(0)            # no host mirror of the sessions when the data came from the device
+    aix = sb.VMISIndex.from_sessions(items, off, ts, m, max_len, 1.3, device=0)   # default: host data, device build
+    assert np.array_equal(aix.items_for_session(0), items[off[0]:off[1]])
+    a = sb.predict_batch(aix, queries, 20, m, 21)
+    b = sb.predict_batch(hix, queries, 20, m, 21)
+    assert all(np.array_equal(x, y) for x, y in zip(a, b))
 
 
 def test_device_synth_matches_host_synth(sb, oracle):
     n_items, n_sessions = 5000, 40000
     six = sb.VMISIndex.synth(42, n_items, n_sessions, 1502, 34, 2.0)
     items, off, ts = sb.synth_sessions(42, n_items, n_sessions)
-    hix = sb.VMISIndex.from_sessions(items, off, ts, 1502, 34, 2.0, device=0)
+    os.environ["VMIS_BUILD"] = "host"
+    try:
+        hix = sb.VMISIndex.from_sessions(items, off, ts, 1502, 34, 2.0, device=0)
+    finally:
+        del os.environ["VMIS_BUILD"]
     ss, hs = six.stats(), hix.stats()
     for key in ("n_sessions_kept", "n_items", "n_pairs_kept", "n_postings"):
         assert ss[key] == hs[key], key
