@@ -318,7 +318,9 @@ def main():
            "warmup": args.warmup, "ms_per_step": total_ms_max / args.steps, "higher_is_better": True,
            "scaling": "weak", "vs_baseline": None, "dtype": "u32/i32+f64", "data": "synthetic", "config": cfg,
            "clocks": clocks, "gpu_launches": args.steps * 1,
-           "e2e": {"value": e2e_value, "unit": "queries/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h},
+           "e2e": {"value": e2e_value, "unit": "queries/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+                   "launches_per_step": (B + (1 << 17) - 1) >> 17,
+                   "note": "vmis_predict_batch pipelines the batch in chunks of 2^17 sessions over 3 streams"},
            "roofline": roofline, "step_ms": [round(x, 3) for x in step_ms]}
 
     if rank == 0 and world == 1 and not args.no_cpu_baseline and items is not None:

@@ -29,12 +29,14 @@ ia, iinst, ith, isamp = h.index("Address"), h.index("Instructions Executed"), h.
 base = int(rows[2][ia], 16)
 src = open(ROOT + "/serenade_b200/csrc/predict_sm100.cu").read().splitlines()
 def find(s):
+    if s.startswith("phase"):     # code markers look like "// ------ phase 2a: ..."; the header comment also names phases
+        return next(i + 1 for i, l in enumerate(src) if re.search(r"// -{10,} " + re.escape(s), l))
     return next(i + 1 for i, l in enumerate(src) if s in l)
 marks = [("helpers (sort/scan/hash)", 1), ("accumulate (phase 2b)", find("struct FlatMap")),
          ("select helpers (u32 net, exact_elem)", find("constexpr int kIdxBits")),
          ("select_topn (phase 3)", find("__device__ __forceinline__ uint32_t select_topn")),
          ("kernel prologue", find("vmis_predict_kernel(const IndexView")),
-         ("phase 0", find("-- phase 0")), ("phase 1 merge", find("-- phase 1")), ("phase 1b top-k", find("-- phase 1b")),
+         ("phase 0", find("phase 0")), ("phase 1 merge", find("phase 1")), ("phase 1b top-k", find("phase 1b")),
          ("neighbours mode", find("if (neighbors_mode) {")), ("phase 2a directory", find("phase 2a")),
          ("phase 2b+3 driver", find("phase 2b + 3")), ("end", find("uint32_t next_pow2"))]
 agg = collections.defaultdict(lambda: [0, 0, 0])
