@@ -110,6 +110,12 @@ vmis_index_t* vmis_index_from_device_sessions(const uint64_t* d_items, const uin
 vmis_index_t* vmis_index_synth(uint64_t seed, uint64_t n_items, uint64_t n_sessions, size_t m, size_t max_len,
                                double idf_weighting, int device, uint32_t shard, uint32_t n_shards);
 
+/* ---- serialised index blob (fast restart; the reference rebuilds from CSV or re-reads Avro at start-up,
+ * serving.rs:37-52).  The blob holds the flat HBM arrays of one handle (one shard).  A loaded handle has no host
+ * mirror of the sessions (vmis_items_for_session / vmis_session_timestamp fail); everything else works. */
+int vmis_index_save(const vmis_index_t* index, const char* path);
+vmis_index_t* vmis_index_load(const char* path, int device);
+
 /* item_to_product_attributes (vmis_index.rs:34; Avro fields ForSale/IsAdult :184-192).  Replaces the
  * attributes of the listed items (flags = VMIS_ATTR_* bits; 0 removes the entry).  Call before serving. */
 int vmis_index_set_attributes(vmis_index_t* index, const uint64_t* items, const uint8_t* flags, size_t n);

@@ -62,6 +62,8 @@ struct vmis_index {
   uint64_t n_sessions_kept = 0;
   uint32_t shard = 0;                        // item-sharded postings: the shard this handle owns
   uint64_t synth_interactions = 0;           // vmis_index_synth: interactions generated on the device
+  uint64_t n_post_entries = 0;               // u32 entries of this handle's posting shard (incl. padding)
+  uint64_t n_sess_item_entries = 0;          // u32 entries of sess_items (incl. padding)
   std::vector<void*> ipc_mapped;             // peer shards opened through CUDA IPC
   std::mutex mu;
   std::vector<std::unique_ptr<CallCtx>> pool;
@@ -158,6 +160,8 @@ vmis_index* finish_index(std::unique_ptr<vmis_index> ix, size_t m, size_t max_le
   V.n_kept = (uint32_t)F.rank_to_orig.size();
   V.m_build = F.m_build;
   V.max_len = F.max_len;
+  ix->n_post_entries = own.size();
+  ix->n_sess_item_entries = F.sess_items.size();
   // the big CSR arrays now live in HBM only
   std::vector<uint32_t>().swap(F.postings);
   std::vector<uint32_t>().swap(F.sess_items);
@@ -182,6 +186,8 @@ vmis_index* adopt_device_index(std::unique_ptr<vmis_index> ix, vmis::DeviceIndex
   V.n_items = (uint32_t)A.n_items; V.n_kept = (uint32_t)A.n_kept; V.m_build = F.m_build; V.max_len = F.max_len;
   void* owned[] = {A.item_key, A.item_hash, A.post_ref, A.postings, A.sess_ref, A.sess_items, A.idf, A.attr, A.rank_to_orig};
   for (void* p : owned) ix->dev_allocs.push_back(p);
+  ix->n_post_entries = A.shard_entries;
+  ix->n_sess_item_entries = A.sess_items_entries;
   ix->device_bytes = A.n_items * 8 + A.item_hash_cap * sizeof(vmis::ItemHashEntry) + A.n_items * 8 + A.shard_entries * 4 +
                      A.n_kept * 8 + A.sess_items_entries * 4 + A.n_items * 9 + A.n_kept * 4;
   return ix.release();
@@ -328,6 +334,23 @@ int host_batch(const vmis_index* cix, const uint64_t* q_items, const uint32_t* q
 
 }  // namespace
 
+namespace {
+struct BlobHeader {
+  char magic[8];                 // "VMISB200"
+  uint32_t version, n_shards, shard, m_build, max_len, pad;
+  uint64_t n_items, hash_cap, n_kept, n_post_entries, n_sess_item_entries, n_pairs_kept, n_postings;
+  double idf_weighting;
+};
+template <class T>
+bool dump_dev(FILE* f, const T* dev, uint64_t n) {
+  std::vector<T> h(n);
+  if (n && cudaMemcpy(h.data(), dev, n * sizeof(T), cudaMemcpyDeviceToHost) != cudaSuccess) return false;
+  return std::fwrite(h.data(), sizeof(T), n, f) == n;
+}
+template <class T>
+bool slurp(FILE* f, std::vector<T>* v, uint64_t n) { v->resize(n); return std::fread(v->data(), sizeof(T), n, f) == n; }
+}  // namespace
+
 extern "C" {
 
 const char* vmis_last_error(void) { return g_err.c_str(); }
@@ -382,6 +405,68 @@ vmis_index_t* vmis_index_synth(uint64_t seed, uint64_t n_items, uint64_t n_sessi
   vmis_index* r = adopt_device_index(std::move(ix), A, m, max_len, idf_weighting, device, shard, n_shards);
   if (r) r->synth_interactions = s.n_entries;
   return r;
+}
+
+// ---- serialised index blob: the "checkpoint" of this path (the reference rebuilds or re-reads Avro at start-up,
+// serving.rs:37-52; loading the flat arrays is a plain read + upload) ----
+int vmis_index_save(const vmis_index_t* ix, const char* path) {
+  if (!ix || !path) return fail(VMIS_ERR_ARG, "NULL argument");
+  if (ix->device == VMIS_DEVICE_NONE) return fail(VMIS_ERR_ARG, "only device-resident indexes can be saved");
+  CU_TRY(cudaSetDevice(ix->device));
+  CU_TRY(cudaDeviceSynchronize());
+  FILE* f = std::fopen(path, "wb");
+  if (!f) return fail(VMIS_ERR_IO, "cannot create %s", path);
+  const vmis::IndexView& V = ix->view;
+  BlobHeader h{};
+  std::memcpy(h.magic, "VMISB200", 8);
+  h.version = 1; h.n_shards = V.n_shards; h.shard = ix->shard; h.m_build = V.m_build; h.max_len = V.max_len;
+  h.n_items = V.n_items; h.hash_cap = (uint64_t)V.item_hash_mask + 1; h.n_kept = V.n_kept;
+  h.n_post_entries = ix->n_post_entries; h.n_sess_item_entries = ix->n_sess_item_entries;
+  h.n_pairs_kept = ix->flat.n_pairs_kept; h.n_postings = ix->flat.n_postings; h.idf_weighting = ix->flat.idf_weighting;
+  bool ok = std::fwrite(&h, sizeof h, 1, f) == 1 && dump_dev(f, V.item_key, h.n_items) && dump_dev(f, V.item_hash, h.hash_cap) &&
+            dump_dev(f, V.post_ref, h.n_items) && dump_dev(f, V.post_shard[ix->shard], h.n_post_entries) &&
+            dump_dev(f, V.sess_ref, h.n_kept) && dump_dev(f, V.sess_items, h.n_sess_item_entries) &&
+            dump_dev(f, V.idf, h.n_items) && dump_dev(f, V.attr, h.n_items) && dump_dev(f, V.rank_to_orig, h.n_kept);
+  ok = (std::fclose(f) == 0) && ok;
+  if (!ok) return fail(VMIS_ERR_IO, "short write to %s", path);
+  return VMIS_OK;
+}
+
+vmis_index_t* vmis_index_load(const char* path, int device) {
+  if (!path) { fail(VMIS_ERR_ARG, "path is NULL"); return nullptr; }
+  FILE* f = std::fopen(path, "rb");
+  if (!f) { fail(VMIS_ERR_IO, "cannot open %s", path); return nullptr; }
+  BlobHeader h{};
+  std::unique_ptr<vmis_index> ix(new vmis_index());
+  vmis::FlatIndex& F = ix->flat;
+  std::vector<uint32_t> own;
+  bool ok = std::fread(&h, sizeof h, 1, f) == 1 && !std::memcmp(h.magic, "VMISB200", 8) && h.version == 1 &&
+            h.n_shards >= 1 && h.n_shards <= (uint32_t)vmis::kMaxShards && h.shard < h.n_shards;
+  ok = ok && slurp(f, &F.item_key, h.n_items) && slurp(f, &F.item_hash, h.hash_cap) && slurp(f, &F.post_ref, h.n_items) &&
+       slurp(f, &own, h.n_post_entries) && slurp(f, &F.sess_ref, h.n_kept) && slurp(f, &F.sess_items, h.n_sess_item_entries) &&
+       slurp(f, &F.idf, h.n_items) && slurp(f, &F.attr, h.n_items) && slurp(f, &F.rank_to_orig, h.n_kept);
+  std::fclose(f);
+  if (!ok) { fail(VMIS_ERR_IO, "%s is not a VMIS index blob (or is truncated)", path); return nullptr; }
+  F.n_pairs_kept = h.n_pairs_kept; F.n_postings = h.n_postings; F.m_build = h.m_build; F.max_len = h.max_len;
+  F.idf_weighting = h.idf_weighting; F.n_shards = h.n_shards;
+  ix->shard = h.shard; ix->n_sessions_kept = h.n_kept; ix->device = device;
+  if (select_device(device, &ix->sm_count) != VMIS_OK) return nullptr;
+  vmis::IndexView& V = ix->view;
+  const uint32_t* own_dev = nullptr;
+  for (int s2 = 0; s2 < vmis::kMaxShards; ++s2) V.post_shard[s2] = nullptr;
+  if (upload(ix.get(), F.item_key, &V.item_key) || upload(ix.get(), F.item_hash, &V.item_hash) ||
+      upload(ix.get(), F.post_ref, &V.post_ref) || upload(ix.get(), own, &own_dev) ||
+      upload(ix.get(), F.sess_ref, &V.sess_ref) || upload(ix.get(), F.sess_items, &V.sess_items) ||
+      upload(ix.get(), F.idf, &V.idf) || upload(ix.get(), F.attr, &V.attr) || upload(ix.get(), F.rank_to_orig, &V.rank_to_orig)) {
+    for (void* d : ix->dev_allocs) cudaFree(d);
+    return nullptr;
+  }
+  V.post_shard[h.shard] = own_dev; V.n_shards = h.n_shards;
+  V.item_hash_mask = (uint32_t)(h.hash_cap - 1); V.n_items = (uint32_t)h.n_items; V.n_kept = (uint32_t)h.n_kept;
+  V.m_build = h.m_build; V.max_len = h.max_len;
+  ix->n_post_entries = h.n_post_entries; ix->n_sess_item_entries = h.n_sess_item_entries;
+  std::vector<uint32_t>().swap(F.sess_items); std::vector<uint2>().swap(F.sess_ref); std::vector<uint2>().swap(F.post_ref);
+  return ix.release();
 }
 
 int vmis_index_export_shard(const vmis_index_t* ix, void* handle64) {

@@ -30,6 +30,7 @@
 
 #include <algorithm>
 #include <cstdio>
+#include <cstdlib>
 
 namespace vmis {
 namespace {
@@ -869,6 +870,7 @@ int plan_launch(const IndexView& ix, uint32_t k, uint32_t m, int sm_count, Launc
   if (total > 227 * 1024) return VMIS_ERR_LIMIT;
   p.smem_bytes = (uint32_t)total;
   int per_sm = (int)std::min<size_t>(5, (227 * 1024) / (total + 1024));   // 1 KB per CTA is reserved by the driver
+  if (const char* e = std::getenv("VMIS_CTAS_PER_SM")) per_sm = std::min(per_sm, std::max(1, std::atoi(e)));   // tuning knob
   if (per_sm < 1) per_sm = 1;
   p.grid = (uint32_t)(sm_count * per_sm);
   p.gtab_cap = next_pow2(std::max(2u * std::max(k, 1u) * std::max(ix.max_len, 1u), 1024u));

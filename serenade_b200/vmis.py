@@ -53,6 +53,8 @@ def load_library():
         "vmis_index_from_sessions_sharded": (vp, [_u64p, _u64p, _u32p, sz, sz, sz, f64, i32, u32, u32]),
         "vmis_index_from_device_sessions": (vp, [vp, vp, vp, sz, sz, sz, f64, i32, u32, u32]),
         "vmis_index_synth": (vp, [u64, u64, u64, sz, sz, f64, i32, u32, u32]),
+        "vmis_index_save": (i32, [vp, C.c_char_p]),
+        "vmis_index_load": (vp, [C.c_char_p, i32]),
         "vmis_index_export_shard": (i32, [vp, vp]),
         "vmis_index_attach_shard": (i32, [vp, u32, vp]),
         "vmis_index_attach_shard_ptr": (i32, [vp, u32, vp]),
@@ -89,7 +91,7 @@ def load_library():
 EXPORTED_SYMBOLS = ("vmis_index_from_csv", "vmis_index_from_csv_ex", "vmis_index_from_sessions",
                     "vmis_index_from_sessions_sharded", "vmis_index_export_shard", "vmis_index_attach_shard",
                     "vmis_index_attach_shard_ptr", "vmis_index_shard_ptr", "vmis_index_from_device_sessions",
-                    "vmis_index_synth",
+                    "vmis_index_synth", "vmis_index_save", "vmis_index_load",
                     "vmis_index_set_attributes", "vmis_index_free", "vmis_index_stats", "vmis_predict_batch",
                     "vmis_predict_batch_device", "vmis_predict", "vmis_find_neighbors_batch", "vmis_items_for_session",
                     "vmis_idf", "vmis_find_attributes", "vmis_postings", "vmis_session_timestamp",
@@ -173,6 +175,14 @@ class VMISIndex:
         L = load_library()
         return cls(L.vmis_index_synth(seed, n_items, n_sessions, m_most_recent_sessions, max_len, float(idf_weighting),
                                       device, shard, n_shards))
+
+    def save(self, path):
+        """serialise the HBM arrays of this handle (fast restart)"""
+        _check(load_library().vmis_index_save(self._h, os.fsencode(path)))
+
+    @classmethod
+    def load(cls, path, device=0):
+        return cls(load_library().vmis_index_load(os.fsencode(path), device))
 
     def export_shard(self):
         buf = C.create_string_buffer(64)

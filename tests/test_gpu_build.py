@@ -97,3 +97,28 @@ def test_device_built_shards(sb):
     for sh in shards:
         got = sb.predict_batch(sh, q, 100, 300, 21)
         assert all(np.array_equal(x, y) for x, y in zip(got, want))
+
+
+def test_save_load_roundtrip(sb, tmp_path):
+    """serialised index blob: loaded handle answers bit-identically; attributes travel; bad files are rejected"""
+    items, off, ts = sb.synth_sessions(42, 3000, 20000)
+    ix = sb.VMISIndex.from_sessions(items, off, ts, 400, 34, 2.0, device=0)
+    known = np.unique(items)
+    ix.set_attributes(known[:50], np.full(50, 6, dtype=np.uint8))       # adult + for sale
+    q = sb.synth_queries(43, 3000, 3000, 4)
+    want = [sb.predict_batch(ix, q, 100, 400, 21, biz) for biz in (False, True)]
+    path = str(tmp_path / "index.vmis")
+    ix.save(path)
+    ld = sb.VMISIndex.load(path)
+    for key in ("n_sessions_kept", "n_items", "n_pairs_kept", "n_postings", "max_len", "m_build", "idf_weighting"):
+        assert ld.stats()[key] == ix.stats()[key], key
+    for biz in (False, True):
+        got = sb.predict_batch(ld, q, 100, 400, 21, biz)
+        assert all(np.array_equal(x, y) for x, y in zip(got, want[biz]))
+    assert ld.idf(int(known[3])) == ix.idf(int(known[3]))
+    assert ld.find_attributes(int(known[3])) == {"is_for_sale": True, "is_adult": True}
+    bad = tmp_path / "bad.vmis"
+    bad.write_bytes(b"not an index")
+    with pytest.raises(sb.VmisError) as e:
+        sb.VMISIndex.load(str(bad))
+    assert e.value.code == -2
