@@ -184,7 +184,7 @@ struct SmemLayout {
 // histogram of phase 1b and the cross-warp candidate buffers of phase 3.
 union Scratch {
   uint32_t hist[kWarps][32];
-  Elem top[kWarps * 32];
+  struct { uint64_t s[kWarps * 32]; uint32_t id[kWarps * 32]; } top;      // exact path: per-warp top-32 lists
   struct { uint32_t top32[kWarps * 32]; uint32_t queue[kWarps][64]; } sel;
 };
 
@@ -457,11 +457,14 @@ __device__ __forceinline__ uint32_t select_topn(const IndexView& ix, const Predi
       const Elem worst = shfl_elem(top, 31);
       if (__any_sync(kFull, better(x, worst))) top = warp_merge_top(top, warp_sort_desc(x, lane), lane);
     }
-    X.top[warp * 32 + lane] = top;
+    X.top.s[warp * 32 + lane] = top.s; X.top.id[warp * 32 + lane] = top.id;
     __syncthreads();
     if (warp == 0) {
-      Elem best = X.top[lane];
-      for (int w = 1; w < kWarps; ++w) best = warp_merge_top(best, X.top[w * 32 + lane], lane);
+      Elem best; best.s = X.top.s[lane]; best.id = X.top.id[lane];
+      for (int w = 1; w < kWarps; ++w) {
+        Elem o; o.s = X.top.s[w * 32 + lane]; o.id = X.top.id[w * 32 + lane];
+        best = warp_merge_top(best, o, lane);
+      }
       const uint32_t valid = __popc(__ballot_sync(kFull, best.id != kEmpty));
       const uint32_t take = min(valid, N - written);
       if ((uint32_t)lane < take) {
@@ -469,11 +472,11 @@ __device__ __forceinline__ uint32_t select_topn(const IndexView& ix, const Predi
         a.out_scores[(size_t)q * N + written + lane] = bits_score(best.s);
       }
       if (lane == 0) S.sel_count = take;
-      if (take > 0) { const Elem lastE = shfl_elem(best, (int)take - 1); if (lane == 0) X.top[0] = lastE; }
+      if (take > 0) { const Elem lastE = shfl_elem(best, (int)take - 1); if (lane == 0) { X.top.s[0] = lastE.s; X.top.id[0] = lastE.id; } }
     }
     __syncthreads();
     const uint32_t emitted = S.sel_count;
-    if (emitted > 0) bound = X.top[0];
+    if (emitted > 0) { bound.s = X.top.s[0]; bound.id = X.top.id[0]; }
     written += emitted;
     first_round = false;
     __syncthreads();
@@ -483,7 +486,7 @@ __device__ __forceinline__ uint32_t select_topn(const IndexView& ix, const Predi
 }
 
 
-__global__ void __launch_bounds__(kThreads, 5)
+__global__ void __launch_bounds__(kThreads, kCtasPerSm)
 vmis_predict_kernel(const IndexView ix, const PredictArgs a, const LaunchPlan plan, const Workspace ws) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   SmemLayout& S = *reinterpret_cast<SmemLayout*>(smem_raw);
@@ -869,7 +872,7 @@ int plan_launch(const IndexView& ix, uint32_t k, uint32_t m, int sm_count, Launc
   const size_t total = fixed + nbr + std::max(std::max(r1, r2), size_t(kMaxSessionLen) * 8) + 16;
   if (total > 227 * 1024) return VMIS_ERR_LIMIT;
   p.smem_bytes = (uint32_t)total;
-  int per_sm = (int)std::min<size_t>(5, (227 * 1024) / (total + 1024));   // 1 KB per CTA is reserved by the driver
+  int per_sm = (int)std::min<size_t>(kCtasPerSm, (227 * 1024) / (total + 1024));   // 1 KB per CTA is reserved by the driver
   if (const char* e = std::getenv("VMIS_CTAS_PER_SM")) per_sm = std::min(per_sm, std::max(1, std::atoi(e)));   // tuning knob
   if (per_sm < 1) per_sm = 1;
   p.grid = (uint32_t)(sm_count * per_sm);

@@ -10,7 +10,14 @@
 namespace vmis {
 
 constexpr uint32_t kEmpty = 0xFFFFFFFFu;
-constexpr int kThreads = 256;            // one CTA per evolving session
+#ifndef VMIS_THREADS
+#define VMIS_THREADS 256
+#endif
+#ifndef VMIS_CTAS
+#define VMIS_CTAS 5
+#endif
+constexpr int kThreads = VMIS_THREADS;   // one CTA per evolving session
+constexpr int kCtasPerSm = VMIS_CTAS;    // resident CTAs per SM the kernel is compiled (register-bounded) for
 constexpr int kWarps = kThreads / 32;
 constexpr int kMaxSessionLen = 128;      // evolving-session length limit of the kernel (reference HPO grid: <= 100)
 constexpr uint32_t kMaxK = 2048;         // keeps the int32 item numerators exact

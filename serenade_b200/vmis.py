@@ -15,7 +15,7 @@ import os
 import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-_LIB_PATH = os.path.join(_HERE, "libvmis_b200.so")
+_LIB_PATH = os.environ.get("VMIS_LIB", os.path.join(_HERE, "libvmis_b200.so"))   # VMIS_LIB: tuning builds only
 
 DEVICE_NONE = -1
 ATTR_EXISTS, ATTR_FOR_SALE, ATTR_ADULT = 1, 2, 4
