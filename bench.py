@@ -314,6 +314,21 @@ def main():
     h2d = int(np.mean([qi.numel() * 8 + qo.numel() * 4 for qi, qo in h_q[args.warmup:]]))
     d2h = B * n * 16 + B * 4
 
+    # single-call latency of the reference's exact call shape (one evolving session, mod.rs:118-125), outside
+    # every timed region; the reference's evaluator prints the same percentiles (evaluator.rs:82-89)
+    lat = []
+    qi0, qo0 = batches[0]
+    ids1 = np.zeros(n, dtype=np.uint64); sc1 = np.zeros(n, dtype=np.float64)
+    for q in range(300):
+        ev = np.ascontiguousarray(qi0[qo0[q]:qo0[q + 1]])
+        t_a = time.perf_counter()
+        lib.vmis_predict(gix.handle, ev.ctypes.data_as(u64p), len(ev), K, M, n, 0, ids1.ctypes.data_as(u64p),
+                         sc1.ctypes.data_as(f64p))
+        lat.append((time.perf_counter() - t_a) * 1e6)
+    lat = np.sort(np.array(lat[50:]))
+    latency = {"single_call_us": {p: round(float(np.percentile(lat, float(p[1:]))), 1) for p in ("p50", "p90", "p99")},
+               "note": "vmis_predict, one evolving session per call, host buffers"}
+
     out = {"metric": METRIC, "value": value, "unit": "queries/s", "n_gpus": world, "steps": args.steps,
            "warmup": args.warmup, "ms_per_step": total_ms_max / args.steps, "higher_is_better": True,
            "scaling": "weak", "vs_baseline": None, "dtype": "u32/i32+f64", "data": "synthetic", "config": cfg,
@@ -321,7 +336,7 @@ def main():
            "e2e": {"value": e2e_value, "unit": "queries/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                    "launches_per_step": (B + (1 << 17) - 1) >> 17,
                    "note": "vmis_predict_batch pipelines the batch in chunks of 2^17 sessions over 3 streams"},
-           "roofline": roofline, "step_ms": [round(x, 3) for x in step_ms]}
+           "roofline": roofline, "step_ms": [round(x, 3) for x in step_ms], "latency": latency}
 
     if rank == 0 and world == 1 and not args.no_cpu_baseline and items is not None:
         from oracle import vmis_oracle as vo

@@ -179,6 +179,25 @@ def test_overflow_table_path(sb, oracle):
     _assert_batch_equal(sb, gix, oix, queries, 288, 1502, 70)
 
 
+def test_global_table_fallback_with_many_distinct_items(sb, oracle):
+    """more distinct neighbour items than the shared score table can hold → the CTA's global table (big k)"""
+    rng = np.random.default_rng(33)
+    n_items, n_sessions = 80_000, 3000
+    items, off = [], [0]
+    for s in range(n_sessions):
+        tail = rng.choice(np.arange(1, n_items), size=29, replace=False)
+        items.extend(sorted([5] + [int(x) * 7 + 13 for x in tail]))       # item 5 is in every session
+        off.append(len(items))
+    items, off = np.array(items, dtype=np.uint64), np.array(off, dtype=np.uint64)
+    ts = rng.permutation(n_sessions).astype(np.uint32)
+    gix = sb.VMISIndex.from_sessions(items, off, ts, 2500, 34, 1.0, device=0)
+    oix = oracle.OracleIndex.from_sessions(items, off, ts, 2500, 34, 1.0)
+    queries = [[5], [int(items[7]), 5], [5, int(items[40]), int(items[41])]] * 3
+    _assert_batch_equal(sb, gix, oix, queries, 2048, 2500, 21)          # ~45 k distinct items per query
+    _assert_batch_equal(sb, gix, oix, queries, 2048, 2500, 100)         # exact path with several rounds
+    _assert_batch_equal(sb, gix, oix, queries, 288, 1502, 21)           # and back to the shared table
+
+
 def test_synthetic_config2_batch1024(sb, oracle):
     """BASELINE.json config 2: synthetic 1M interactions / 50k items, batch = 1024 query sessions"""
     items, off, ts = sb.synth_sessions(42, 50_000, 193_000)
