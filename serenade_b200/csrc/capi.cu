@@ -41,9 +41,11 @@ struct CallCtx {
   void* buf = nullptr; size_t buf_cap = 0;
   void* ws = nullptr; size_t ws_cap = 0;
   uint32_t ws_grid = 0, ws_gtab_cap = 0;   // geometry the workspace tables were initialised for
+  void* pinned = nullptr; size_t pinned_cap = 0;   // host staging of small batches (one copy each way)
   ~CallCtx() {
     if (buf) cudaFree(buf);
     if (ws) cudaFree(ws);
+    if (pinned) cudaFreeHost(pinned);
     if (done) cudaEventDestroy(done);
     if (stream) cudaStreamDestroy(stream);
   }
@@ -288,6 +290,42 @@ int host_batch(const vmis_index* cix, const uint64_t* q_items, const uint32_t* q
       if (r) return r;
       r = ensure(&c->buf, &c->buf_cap, total);
       if (r) return r;
+    }
+    // latency path: a small batch is staged through pinned memory, one copy in, one launch, one copy out
+    if (!stream_ && n_chunks == 1 && total <= (size_t(1) << 20)) {
+      CallCtx* c = ring[0].get();
+      if (c->pinned_cap < total) {
+        if (c->pinned) { CU_TRY(cudaFreeHost(c->pinned)); c->pinned = nullptr; c->pinned_cap = 0; }
+        CU_TRY(cudaHostAlloc(&c->pinned, size_t(1) << 20, cudaHostAllocDefault));
+        c->pinned_cap = size_t(1) << 20;
+      }
+      unsigned char* b = static_cast<unsigned char*>(c->buf);
+      unsigned char* p = static_cast<unsigned char*>(c->pinned);
+      const size_t ni = q_off[n_q];
+      if (ni) std::memcpy(p + o_items, q_items, ni * 8);
+      std::memcpy(p + o_off, q_off, (size_t(n_q) + 1) * 4);
+      CU_TRY(cudaStreamWaitEvent(c->stream, c->done, 0));
+      CU_TRY(cudaMemcpyAsync(b, p, o_ids, cudaMemcpyHostToDevice, c->stream));
+      vmis::PredictArgs a{};
+      a.q_items = reinterpret_cast<const uint64_t*>(b + o_items);
+      a.q_off = reinterpret_cast<const uint32_t*>(b + o_off);
+      a.n_q = n_q; a.k = k; a.m = m; a.how_many = how_many; a.biz = biz;
+      a.out_counts = reinterpret_cast<uint32_t*>(b + o_cnt);
+      if (nb_mode) { a.out_sess = reinterpret_cast<uint32_t*>(b + o_ids); a.out_sim = reinterpret_cast<double*>(b + o_sc); }
+      else { a.out_ids = reinterpret_cast<uint64_t*>(b + o_ids); a.out_scores = reinterpret_cast<double*>(b + o_sc); }
+      int r = run_device(ix, c, a, plan, c->stream);
+      if (r) return r;
+      CU_TRY(cudaMemcpyAsync(p + o_ids, b + o_ids, total - o_ids, cudaMemcpyDeviceToHost, c->stream));
+      CU_TRY(cudaEventRecord(c->done, c->stream));
+      CU_TRY(cudaStreamSynchronize(c->stream));
+      if (nb_mode) {
+        if (k) { std::memcpy(out_sess, p + o_ids, size_t(n_q) * k * 4); std::memcpy(out_sim, p + o_sc, size_t(n_q) * k * 8); }
+      } else if (how_many) {
+        std::memcpy(out_ids, p + o_ids, size_t(n_q) * how_many * 8);
+        std::memcpy(out_scores, p + o_sc, size_t(n_q) * how_many * 8);
+      }
+      std::memcpy(out_counts, p + o_cnt, size_t(n_q) * 4);
+      return VMIS_OK;
     }
     for (uint32_t ch = 0; ch < n_chunks; ++ch) {
       CallCtx* c = ring[ch % n_ctx].get();

@@ -29,6 +29,7 @@
 #include "vmis_device.h"
 
 #include <algorithm>
+#include <atomic>
 #include <cstdio>
 #include <cstdlib>
 
@@ -848,6 +849,11 @@ vmis_predict_kernel(const IndexView ix, const PredictArgs a, const LaunchPlan pl
       }
     }
   }
+  // the last CTA to leave re-arms the work counter for the next launch on this workspace (no memset per launch)
+  if (tid == 0) {
+    __threadfence();
+    if (atomicAdd(ws.counter + 1, 1u) == gridDim.x - 1) { ws.counter[0] = 0u; ws.counter[1] = 0u; __threadfence(); }
+  }
 }
 
 uint32_t next_pow2(uint32_t x) { uint32_t p = 1; while (p < x) p <<= 1; return p; }
@@ -899,7 +905,9 @@ Workspace carve_workspace(void* base, const LaunchPlan& plan) {
 
 cudaError_t init_workspace(const Workspace& ws, cudaStream_t stream) {
   const size_t n = size_t(ws.grid) * ws.gtab_cap;
-  cudaError_t e = cudaMemsetAsync(ws.gtab_keys, 0xFF, n * 4, stream);
+  cudaError_t e = cudaMemsetAsync(ws.counter, 0, 2 * sizeof(uint32_t), stream);   // work counter + exit counter
+  if (e != cudaSuccess) return e;
+  e = cudaMemsetAsync(ws.gtab_keys, 0xFF, n * 4, stream);
   if (e != cudaSuccess) return e;
   return cudaMemsetAsync(ws.gtab_vals, 0, n * 4, stream);
 }
@@ -907,11 +915,17 @@ cudaError_t init_workspace(const Workspace& ws, cudaStream_t stream) {
 cudaError_t launch_predict(const IndexView& ix, const PredictArgs& args, const LaunchPlan& plan, const Workspace& ws,
                            cudaStream_t stream) {
   if (args.n_q == 0) return cudaSuccess;
-  cudaError_t e = cudaFuncSetAttribute(vmis_predict_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                       (int)plan.smem_bytes);
+  // the dynamic shared memory opt-in is per device and sticky: raise it only when a larger plan shows up
+  static std::atomic<int> smem_opt_in[64];
+  int dev = 0;
+  cudaError_t e = cudaGetDevice(&dev);
   if (e != cudaSuccess) return e;
-  e = cudaMemsetAsync(ws.counter, 0, sizeof(uint32_t), stream);
-  if (e != cudaSuccess) return e;
+  std::atomic<int>& cur = smem_opt_in[dev & 63];
+  if ((int)plan.smem_bytes > cur.load(std::memory_order_relaxed)) {
+    e = cudaFuncSetAttribute(vmis_predict_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)plan.smem_bytes);
+    if (e != cudaSuccess) return e;
+    cur.store((int)plan.smem_bytes, std::memory_order_relaxed);
+  }
   const uint32_t grid = std::min(plan.grid, args.n_q);
   vmis_predict_kernel<<<grid, kThreads, plan.smem_bytes, stream>>>(ix, args, plan, ws);
   return cudaGetLastError();

@@ -82,7 +82,7 @@ struct PredictArgs {
 // overflow score table per resident CTA.  Invariant: between launches every table
 // slot is {kEmpty, 0} (init_workspace() establishes it, the kernel restores it).
 struct Workspace {
-  uint32_t* counter;          // 1 × u32, zeroed by the launcher
+  uint32_t* counter;          // [0] work counter, [1] exit counter; zero between launches (the last CTA re-arms them)
   uint32_t* gtab_keys;        // grid × gtab_cap
   int32_t* gtab_vals;         // grid × gtab_cap
   uint32_t* gtab_occ;         // grid × gtab_cap / 2: occupied-slot lists
@@ -108,7 +108,7 @@ size_t workspace_bytes(const LaunchPlan& plan);
 Workspace carve_workspace(void* base, const LaunchPlan& plan);
 // One-time initialisation of a freshly carved workspace (enqueued on `stream`).
 cudaError_t init_workspace(const Workspace& ws, cudaStream_t stream);
-// Enqueues counter reset + the predict kernel on `stream`.
+// Enqueues the predict kernel on `stream` (the workspace must have been initialised once).
 cudaError_t launch_predict(const IndexView& ix, const PredictArgs& args, const LaunchPlan& plan, const Workspace& ws,
                            cudaStream_t stream);
 // number of kernels launch_predict enqueues (bench "gpu_launches")
