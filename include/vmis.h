@@ -58,6 +58,17 @@ typedef struct vmis_stats {
   double idf_weighting;
 } vmis_stats_t;
 
+/* Report of a pre-computed index load (vmis_index_from_avro / vmis_index_from_parts). */
+typedef struct vmis_prebuilt_info {
+  uint64_t item_files, session_files;      /* .avro files read under itemindex/ and sessionindex/              */
+  uint64_t item_records, session_records;  /* records decoded (before "last record of a key wins")             */
+  uint64_t lists_reordered;                /* posting lists not in (timestamp desc, session idx desc) order     */
+  uint64_t duplicate_postings;             /* repeated session ids dropped from posting lists                   */
+  uint32_t m_carry;                        /* m <= m_carry: first-match positions are carried through the list  */
+                                           /* merges; larger m scans the item lists like mod.rs:133-138         */
+  uint32_t prebuilt;                       /* 1 = the handle was made from pre-computed parts                   */
+} vmis_prebuilt_info_t;
+
 /* Per-query work counters written by the kernel when requested (bench: exact
  * algorithmic bytes per SURVEY.md §8d). */
 typedef struct vmis_query_stats {
@@ -109,6 +120,24 @@ vmis_index_t* vmis_index_from_device_sessions(const uint64_t* d_items, const uin
 /* vmis_synth_sessions generated and indexed entirely on the device (BASELINE configs 4-5). */
 vmis_index_t* vmis_index_synth(uint64_t seed, uint64_t n_items, uint64_t n_sessions, size_t m, size_t max_len,
                                double idf_weighting, int device, uint32_t shard, uint32_t n_shards);
+
+/* VMISIndex::new(base_path) (vmis_index.rs:85-313): loads the production on-disk index — Avro object container
+ * files under <base_path>/itemindex/ ({ItemId, session_indices_time_ordered, idf, ForSale, IsAdult}, :184-192) and
+ * <base_path>/sessionindex/ ({SessionIndex, item_ids_asc, Time}, :249-255); codecs null / deflate / snappy.
+ * Posting lists, idf values and attributes are taken as stored (nothing is recomputed from the sessions).
+ * Lists are normalised to the canonical (timestamp desc, session idx desc) order; data on which the reference
+ * would panic at query time (a posting naming a missing session, a session item without an itemindex record)
+ * fails the load.  VMIS_DEVICE_NONE gives a host-only handle (accessors only). */
+vmis_index_t* vmis_index_from_avro(const char* base_path, int device);
+vmis_index_t* vmis_index_from_avro_sharded(const char* base_path, int device, uint32_t shard, uint32_t n_shards);
+/* The same from arrays in memory: item i has ids item_ids[i], posting list post_sessions[post_off[i] ..
+ * post_off[i+1]) (session indices), idf[i] and attr[i] (VMIS_ATTR_* bits; NULL = for sale, not adult); sessions
+ * are dense by session index like session_to_items_sorted / session_to_max_time_stamp (:28-35). */
+vmis_index_t* vmis_index_from_parts(const uint64_t* item_ids, const uint64_t* post_off, const uint32_t* post_sessions,
+                                    const double* idf, const uint8_t* attr_or_null, size_t n_items, const uint64_t* items,
+                                    const uint64_t* sess_off, const uint32_t* sess_ts, size_t n_sessions, int device,
+                                    uint32_t shard, uint32_t n_shards);
+int vmis_index_prebuilt_info(const vmis_index_t* index, vmis_prebuilt_info_t* out);
 
 /* ---- serialised index blob (fast restart; the reference rebuilds from CSV or re-reads Avro at start-up,
  * serving.rs:37-52).  The blob holds the flat HBM arrays of one handle (one shard).  A loaded handle has no host

@@ -2,6 +2,7 @@
 //
 // Same names, argument meaning and error behaviour as the reference (file:line under the reference tree):
 //   vmis::VMISIndex::new_from_csv(path, m_most_recent_sessions, idf_weighting)   src/vmisknn/vmis_index.rs:38
+//   vmis::VMISIndex::new_(base_path)   [`new` is a C++ keyword]                 src/vmisknn/vmis_index.rs:85
 //   trait SimilarityComputationNew { items_for_session, idf, find_neighbors, find_attributes }
 //                                                                                src/vmisknn/similarity_indexed.rs:8-24
 //   vmis::predict(index, evolving_session, k, m, how_many, enable_business_logic) src/vmisknn/mod.rs:118-125
@@ -34,6 +35,10 @@ class VMISIndex {
   static VMISIndex new_from_csv(const std::string& path_to_training, size_t m_most_recent_sessions, double idf_weighting,
                                 int device = 0) {
     return VMISIndex(vmis_index_from_csv(path_to_training.c_str(), m_most_recent_sessions, idf_weighting, device));
+  }
+  // VMISIndex::new — vmis_index.rs:85: <base_path>/itemindex/*.avro + <base_path>/sessionindex/*.avro
+  static VMISIndex new_(const std::string& base_path, int device = 0) {
+    return VMISIndex(vmis_index_from_avro(base_path.c_str(), device));
   }
   // prepare_hashmap + struct assembly — vmis_index.rs:422, :75-82
   static VMISIndex from_sessions(const std::vector<std::vector<uint64_t>>& historical_sessions,

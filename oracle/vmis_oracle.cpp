@@ -508,6 +508,33 @@ void* vo_index_from_csv(const char* path, size_t m, double idf_w, size_t max_len
   return ix;
 }
 
+// VMISIndex::new (vmis_index.rs:85-313): the index as loaded from Avro — posting lists, idf and attributes are
+// taken as given (:214-226), sessions are dense by SessionIndex (:289-290).  attr bits: 1 exists, 2 for sale, 4 adult.
+void* vo_index_from_parts(const uint64_t* item_ids, const uint64_t* post_off, const uint32_t* post_sessions,
+                          const double* idf, const uint8_t* attr, size_t n_items, const uint64_t* items,
+                          const uint64_t* off, const uint32_t* ts, size_t S) {
+  Index* ix = new Index();
+  ix->session_to_items_sorted.resize(S); ix->session_to_max_time_stamp.assign(ts, ts + S);
+  for (size_t s = 0; s < S; ++s) ix->session_to_items_sorted[s].assign(items + off[s], items + off[s + 1]);
+  ix->item_slot.init(n_items + 8);
+  for (size_t i = 0; i < n_items; ++i) {
+    bool existed = false;
+    uint32_t* slot = ix->item_slot.insert(item_ids[i], (uint32_t)ix->item_ids.size(), &existed);
+    if (!existed) {
+      ix->item_ids.push_back(item_ids[i]); ix->item_to_top_sessions_ordered.emplace_back();
+      ix->item_to_idf_score.push_back(0.0); ix->item_to_product_attributes.push_back(Attr{false, true}); ix->item_has_attr.push_back(1);
+    }
+    const uint32_t d = *slot;                                           // HashMap::insert: a later record replaces
+    ix->item_to_top_sessions_ordered[d].assign(post_sessions + post_off[i], post_sessions + post_off[i + 1]);
+    ix->item_to_idf_score[d] = idf[i];
+    const uint8_t a = attr ? attr[i] : (uint8_t)3;
+    ix->item_has_attr[d] = (a & 1) ? 1 : 0;
+    ix->item_to_product_attributes[d] = Attr{(a & 4) != 0, (a & 2) != 0};
+  }
+  for (auto& v : ix->session_to_items_sorted) { ix->kept_pairs += v.size(); ix->max_training_session_length = std::max(ix->max_training_session_length, v.size()); }
+  return ix;
+}
+
 void vo_index_free(void* h) { delete (Index*)h; }
 
 size_t vo_num_sessions(const void* h) { return ((const Index*)h)->session_to_items_sorted.size(); }

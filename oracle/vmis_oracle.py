@@ -37,6 +37,9 @@ def lib():
         L.vo_index_from_sessions.argtypes = [u64p, u64p, u32p, C.c_size_t, C.c_size_t, C.c_size_t, C.c_double]
         L.vo_index_from_csv.restype = C.c_void_p
         L.vo_index_from_csv.argtypes = [C.c_char_p, C.c_size_t, C.c_double, C.c_size_t]
+        L.vo_index_from_parts.restype = C.c_void_p
+        L.vo_index_from_parts.argtypes = [u64p, u64p, u32p, f64p, C.POINTER(C.c_uint8), C.c_size_t, u64p, u64p, u32p,
+                                          C.c_size_t]
         L.vo_index_free.argtypes = [C.c_void_p]
         for f in ("vo_num_sessions", "vo_num_items", "vo_kept_pairs", "vo_max_len"):
             getattr(L, f).restype = C.c_size_t
@@ -89,6 +92,22 @@ class OracleIndex:
         ts = np.ascontiguousarray(ts, dtype=np.uint32)
         return cls(lib().vo_index_from_sessions(_p(items, C.c_uint64), _p(off, C.c_uint64), _p(ts, C.c_uint32),
                                                 len(ts), m, max_len, float(idf_weighting)))
+
+    @classmethod
+    def from_parts(cls, item_ids, post_off, post_sessions, idf, attr, items, off, ts):
+        """VMISIndex::new (vmis_index.rs:85-313): pre-computed posting lists / idf / attributes, dense sessions."""
+        item_ids = np.ascontiguousarray(item_ids, dtype=np.uint64)
+        post_off = np.ascontiguousarray(post_off, dtype=np.uint64)
+        post_sessions = np.ascontiguousarray(post_sessions, dtype=np.uint32)
+        idf = np.ascontiguousarray(idf, dtype=np.float64)
+        attr = None if attr is None else np.ascontiguousarray(attr, dtype=np.uint8)
+        items = np.ascontiguousarray(items, dtype=np.uint64)
+        off = np.ascontiguousarray(off, dtype=np.uint64)
+        ts = np.ascontiguousarray(ts, dtype=np.uint32)
+        return cls(lib().vo_index_from_parts(_p(item_ids, C.c_uint64), _p(post_off, C.c_uint64),
+                                             _p(post_sessions, C.c_uint32), _p(idf, C.c_double),
+                                             None if attr is None else _p(attr, C.c_uint8), len(item_ids),
+                                             _p(items, C.c_uint64), _p(off, C.c_uint64), _p(ts, C.c_uint32), len(ts)))
 
     def __del__(self):
         if getattr(self, "_h", None) and _lib is not None:

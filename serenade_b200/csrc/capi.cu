@@ -14,6 +14,7 @@
 #include <string>
 #include <vector>
 
+#include "avro_reader.h"
 #include "build_device.h"
 #include "vmis_host.h"
 
@@ -67,6 +68,7 @@ struct vmis_index {
   uint64_t n_post_entries = 0;               // u32 entries of this handle's posting shard (incl. padding)
   uint64_t n_sess_item_entries = 0;          // u32 entries of sess_items (incl. padding)
   std::vector<void*> ipc_mapped;             // peer shards opened through CUDA IPC
+  vmis_prebuilt_info_t prebuilt{};           // pre-computed (Avro / parts) index: load and normalisation report
   std::mutex mu;
   std::vector<std::unique_ptr<CallCtx>> pool;
 };
@@ -102,6 +104,7 @@ int select_device(int device, int* sm_count) {
 
 vmis_index* adopt_device_index(std::unique_ptr<vmis_index> ix, vmis::DeviceIndexArrays& A, size_t m, size_t max_len,
                                double idf_w, int device, uint32_t shard, uint32_t n_shards);
+vmis_index* upload_flat(std::unique_ptr<vmis_index> ix, int device, uint32_t shard, uint32_t n_shards);
 
 // Sessions held on the host → index.  With a device the build itself runs there (build_sm100.cu: ~0.1 s for 60 M
 // interactions instead of ~10 s on one host core; the reference rebuilds the index for every HPO trial,
@@ -136,6 +139,11 @@ vmis_index* finish_index(std::unique_ptr<vmis_index> ix, size_t m, size_t max_le
     cudaGetLastError();   // e.g. out of memory during the sorts: fall through to the host builder
   }
   if (!vmis::build_flat_index(ix->sessions, m, max_len, idf_w, n_shards, &ix->flat, &err)) { fail(VMIS_ERR_ARG, "%s", err.c_str()); return nullptr; }
+  return upload_flat(std::move(ix), device, shard, n_shards);
+}
+
+// FlatIndex (host) → HBM; VMIS_DEVICE_NONE keeps a host-only handle
+vmis_index* upload_flat(std::unique_ptr<vmis_index> ix, int device, uint32_t shard, uint32_t n_shards) {
   ix->shard = shard;
   ix->n_sessions_kept = ix->flat.rank_to_orig.size();
   ix->device = device;
@@ -161,6 +169,7 @@ vmis_index* finish_index(std::unique_ptr<vmis_index> ix, size_t m, size_t max_le
   V.n_items = (uint32_t)F.item_key.size();
   V.n_kept = (uint32_t)F.rank_to_orig.size();
   V.m_build = F.m_build;
+  V.m_carry = F.m_carry;
   V.max_len = F.max_len;
   ix->n_post_entries = own.size();
   ix->n_sess_item_entries = F.sess_items.size();
@@ -178,14 +187,14 @@ vmis_index* adopt_device_index(std::unique_ptr<vmis_index> ix, vmis::DeviceIndex
   F.item_key.swap(A.host_item_key); F.item_hash.swap(A.host_item_hash); F.idf.swap(A.host_idf);
   F.attr.assign(A.n_items, (uint8_t)(VMIS_ATTR_EXISTS | VMIS_ATTR_FOR_SALE));
   F.n_pairs_kept = A.n_pairs_kept; F.n_postings = A.n_postings; F.n_shards = n_shards;
-  F.m_build = (uint32_t)std::min<size_t>(m, 0xFFFFFFFFu); F.max_len = (uint32_t)max_len; F.idf_weighting = idf_w;
+  F.m_build = (uint32_t)std::min<size_t>(m, 0xFFFFFFFFu); F.m_carry = F.m_build; F.max_len = (uint32_t)max_len; F.idf_weighting = idf_w;
   ix->n_sessions_kept = A.n_kept; ix->device = device; ix->shard = shard;
   vmis::IndexView& V = ix->view;
   for (int s2 = 0; s2 < vmis::kMaxShards; ++s2) V.post_shard[s2] = nullptr;
   V.item_key = A.item_key; V.item_hash = A.item_hash; V.item_hash_mask = (uint32_t)(A.item_hash_cap - 1);
   V.post_ref = A.post_ref; V.post_shard[shard] = A.postings; V.n_shards = n_shards;
   V.sess_ref = A.sess_ref; V.sess_items = A.sess_items; V.idf = A.idf; V.attr = A.attr; V.rank_to_orig = A.rank_to_orig;
-  V.n_items = (uint32_t)A.n_items; V.n_kept = (uint32_t)A.n_kept; V.m_build = F.m_build; V.max_len = F.max_len;
+  V.n_items = (uint32_t)A.n_items; V.n_kept = (uint32_t)A.n_kept; V.m_build = F.m_build; V.m_carry = F.m_carry; V.max_len = F.max_len;
   void* owned[] = {A.item_key, A.item_hash, A.post_ref, A.postings, A.sess_ref, A.sess_items, A.idf, A.attr, A.rank_to_orig};
   for (void* p : owned) ix->dev_allocs.push_back(p);
   ix->n_post_entries = A.shard_entries;
@@ -375,7 +384,7 @@ int host_batch(const vmis_index* cix, const uint64_t* q_items, const uint32_t* q
 namespace {
 struct BlobHeader {
   char magic[8];                 // "VMISB200"
-  uint32_t version, n_shards, shard, m_build, max_len, pad;
+  uint32_t version, n_shards, shard, m_build, max_len, m_carry;   // m_carry: version >= 2 (version 1 blobs: = m_build)
   uint64_t n_items, hash_cap, n_kept, n_post_entries, n_sess_item_entries, n_pairs_kept, n_postings;
   double idf_weighting;
 };
@@ -445,6 +454,56 @@ vmis_index_t* vmis_index_synth(uint64_t seed, uint64_t n_items, uint64_t n_sessi
   return r;
 }
 
+// ---- pre-computed index (VMISIndex::new, vmis_index.rs:85-313): posting lists, idf and attributes are taken as given ----
+static vmis_index_t* finish_prebuilt(std::unique_ptr<vmis_index> ix, vmis::PrebuiltIndex& P, int device, uint32_t shard, uint32_t n_shards) {
+  if (n_shards == 0 || shard >= n_shards) { fail(VMIS_ERR_ARG, "shard %u out of range [0,%u)", shard, n_shards); return nullptr; }
+  vmis::PrebuiltInfo pi; std::string err;
+  if (!vmis::build_flat_index_prebuilt(P, n_shards, &ix->flat, &pi, &err)) { fail(VMIS_ERR_ARG, "%s", err.c_str()); return nullptr; }
+  ix->sessions.items.swap(P.sessions.items); ix->sessions.off.swap(P.sessions.off); ix->sessions.ts.swap(P.sessions.ts);
+  ix->prebuilt.prebuilt = 1; ix->prebuilt.lists_reordered = pi.lists_reordered;
+  ix->prebuilt.duplicate_postings = pi.duplicate_postings; ix->prebuilt.m_carry = pi.m_carry;
+  return upload_flat(std::move(ix), device, shard, n_shards);
+}
+
+vmis_index_t* vmis_index_from_avro_sharded(const char* base_path, int device, uint32_t shard, uint32_t n_shards) {
+  if (!base_path) { fail(VMIS_ERR_ARG, "path is NULL"); return nullptr; }
+  std::unique_ptr<vmis_index> ix(new vmis_index());
+  vmis::PrebuiltIndex P; vmis::AvroLoadInfo li; std::string err;
+  if (!vmis::read_index_from_avro(base_path, &P, &li, &err)) { fail(VMIS_ERR_IO, "%s", err.c_str()); return nullptr; }
+  ix->prebuilt.item_files = li.item_files; ix->prebuilt.session_files = li.session_files;
+  ix->prebuilt.item_records = li.item_records; ix->prebuilt.session_records = li.session_records;
+  return finish_prebuilt(std::move(ix), P, device, shard, n_shards);
+}
+
+vmis_index_t* vmis_index_from_avro(const char* base_path, int device) { return vmis_index_from_avro_sharded(base_path, device, 0, 1); }
+
+vmis_index_t* vmis_index_from_parts(const uint64_t* item_ids, const uint64_t* post_off, const uint32_t* post_sessions,
+                                    const double* idf, const uint8_t* attr_or_null, size_t n_items, const uint64_t* items,
+                                    const uint64_t* sess_off, const uint32_t* sess_ts, size_t n_sessions, int device,
+                                    uint32_t shard, uint32_t n_shards) {
+  if (!item_ids || !post_off || !idf || !sess_off || !sess_ts || (!post_sessions && n_items && post_off[n_items] > 0) ||
+      (!items && n_sessions && sess_off[n_sessions] > 0)) { fail(VMIS_ERR_ARG, "NULL index arrays"); return nullptr; }
+  std::unique_ptr<vmis_index> ix(new vmis_index());
+  vmis::PrebuiltIndex P;
+  P.item_ids.assign(item_ids, item_ids + n_items);
+  P.post_off.assign(post_off, post_off + n_items + 1);
+  P.post_sessions.assign(post_sessions, post_sessions + post_off[n_items]);
+  P.idf.assign(idf, idf + n_items);
+  if (attr_or_null) { P.attr.assign(attr_or_null, attr_or_null + n_items); for (auto& a : P.attr) a = a ? (uint8_t)(a | VMIS_ATTR_EXISTS) : 0; }
+  else P.attr.assign(n_items, (uint8_t)(VMIS_ATTR_EXISTS | VMIS_ATTR_FOR_SALE));
+  P.sessions.off.assign(sess_off, sess_off + n_sessions + 1);
+  P.sessions.ts.assign(sess_ts, sess_ts + n_sessions);
+  P.sessions.items.assign(items, items + sess_off[n_sessions]);
+  return finish_prebuilt(std::move(ix), P, device, shard, n_shards);
+}
+
+int vmis_index_prebuilt_info(const vmis_index_t* ix, vmis_prebuilt_info_t* out) {
+  if (!ix || !out) return fail(VMIS_ERR_ARG, "NULL argument");
+  *out = ix->prebuilt;
+  if (!ix->prebuilt.prebuilt) out->m_carry = ix->flat.m_carry;
+  return VMIS_OK;
+}
+
 // ---- serialised index blob: the "checkpoint" of this path (the reference rebuilds or re-reads Avro at start-up,
 // serving.rs:37-52; loading the flat arrays is a plain read + upload) ----
 int vmis_index_save(const vmis_index_t* ix, const char* path) {
@@ -457,7 +516,7 @@ int vmis_index_save(const vmis_index_t* ix, const char* path) {
   const vmis::IndexView& V = ix->view;
   BlobHeader h{};
   std::memcpy(h.magic, "VMISB200", 8);
-  h.version = 1; h.n_shards = V.n_shards; h.shard = ix->shard; h.m_build = V.m_build; h.max_len = V.max_len;
+  h.version = 2; h.n_shards = V.n_shards; h.shard = ix->shard; h.m_build = V.m_build; h.max_len = V.max_len; h.m_carry = V.m_carry;
   h.n_items = V.n_items; h.hash_cap = (uint64_t)V.item_hash_mask + 1; h.n_kept = V.n_kept;
   h.n_post_entries = ix->n_post_entries; h.n_sess_item_entries = ix->n_sess_item_entries;
   h.n_pairs_kept = ix->flat.n_pairs_kept; h.n_postings = ix->flat.n_postings; h.idf_weighting = ix->flat.idf_weighting;
@@ -478,14 +537,15 @@ vmis_index_t* vmis_index_load(const char* path, int device) {
   std::unique_ptr<vmis_index> ix(new vmis_index());
   vmis::FlatIndex& F = ix->flat;
   std::vector<uint32_t> own;
-  bool ok = std::fread(&h, sizeof h, 1, f) == 1 && !std::memcmp(h.magic, "VMISB200", 8) && h.version == 1 &&
+  bool ok = std::fread(&h, sizeof h, 1, f) == 1 && !std::memcmp(h.magic, "VMISB200", 8) && (h.version == 1 || h.version == 2) &&
             h.n_shards >= 1 && h.n_shards <= (uint32_t)vmis::kMaxShards && h.shard < h.n_shards;
   ok = ok && slurp(f, &F.item_key, h.n_items) && slurp(f, &F.item_hash, h.hash_cap) && slurp(f, &F.post_ref, h.n_items) &&
        slurp(f, &own, h.n_post_entries) && slurp(f, &F.sess_ref, h.n_kept) && slurp(f, &F.sess_items, h.n_sess_item_entries) &&
        slurp(f, &F.idf, h.n_items) && slurp(f, &F.attr, h.n_items) && slurp(f, &F.rank_to_orig, h.n_kept);
   std::fclose(f);
   if (!ok) { fail(VMIS_ERR_IO, "%s is not a VMIS index blob (or is truncated)", path); return nullptr; }
-  F.n_pairs_kept = h.n_pairs_kept; F.n_postings = h.n_postings; F.m_build = h.m_build; F.max_len = h.max_len;
+  if (h.version == 1) h.m_carry = h.m_build;
+  F.n_pairs_kept = h.n_pairs_kept; F.n_postings = h.n_postings; F.m_build = h.m_build; F.m_carry = h.m_carry; F.max_len = h.max_len;
   F.idf_weighting = h.idf_weighting; F.n_shards = h.n_shards;
   ix->shard = h.shard; ix->n_sessions_kept = h.n_kept; ix->device = device;
   if (select_device(device, &ix->sm_count) != VMIS_OK) return nullptr;
@@ -501,7 +561,7 @@ vmis_index_t* vmis_index_load(const char* path, int device) {
   }
   V.post_shard[h.shard] = own_dev; V.n_shards = h.n_shards;
   V.item_hash_mask = (uint32_t)(h.hash_cap - 1); V.n_items = (uint32_t)h.n_items; V.n_kept = (uint32_t)h.n_kept;
-  V.m_build = h.m_build; V.max_len = h.max_len;
+  V.m_build = h.m_build; V.m_carry = h.m_carry; V.max_len = h.max_len;
   ix->n_post_entries = h.n_post_entries; ix->n_sess_item_entries = h.n_sess_item_entries;
   std::vector<uint32_t>().swap(F.sess_items); std::vector<uint2>().swap(F.sess_ref); std::vector<uint2>().swap(F.post_ref);
   return ix.release();

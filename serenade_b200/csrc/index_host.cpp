@@ -3,6 +3,7 @@
 // (vmis_index.rs:693-716) and the CSR builder that replaces prepare_hashmap
 // (vmis_index.rs:422-528) with the flat, time-ranked layout of vmis_device.h.
 #include "vmis_host.h"
+#include "avro_reader.h"
 
 #include <algorithm>
 #include <cmath>
@@ -176,6 +177,7 @@ bool build_flat_index(const Sessions& s, size_t m, size_t max_len, double idf_we
   FlatIndex& F = *out;
   F = FlatIndex();
   F.m_build = (uint32_t)std::min<size_t>(m, 0xFFFFFFFFu);
+  F.m_carry = F.m_build;
   F.max_len = (uint32_t)std::min<size_t>(max_len, 0xFFFFFFFFu);
   F.idf_weighting = idf_weighting;
   F.n_shards = n_shards;
@@ -282,6 +284,155 @@ bool build_flat_index(const Sessions& s, size_t m, size_t max_len, double idf_we
     while (F.item_hash[h].val != kEmpty) h = (h + 1) & (uint32_t)(cap - 1);
     F.item_hash[h] = ItemHashEntry{F.item_key[d], (uint32_t)d, 0};
   }
+  return true;
+}
+
+// VMISIndex::new (vmis_index.rs:85-313) hands the query path posting lists, idf and attributes that were
+// computed offline; this turns them into the flat, time-ranked layout of vmis_device.h and checks the
+// properties the kernel's closed forms rely on (see avro_reader.h::PrebuiltInfo).
+bool build_flat_index_prebuilt(const PrebuiltIndex& p, uint32_t n_shards, FlatIndex* out, PrebuiltInfo* info,
+                               std::string* err) {
+  const Sessions& s = p.sessions;
+  const size_t S = s.size(), I = p.item_ids.size();
+  if (S >= 0xFFFFFFFFull || I >= 0xFFFFFFFFull) { *err = "too many sessions / items"; return false; }
+  if (I == 0) { *err = "no item records"; return false; }
+  if (n_shards == 0 || n_shards > (uint32_t)kMaxShards) { *err = "n_shards must be in [1, 8]"; return false; }
+  if (p.post_off.size() != I + 1 || p.idf.size() != I || p.attr.size() != I) { *err = "inconsistent item arrays"; return false; }
+  FlatIndex& F = *out;
+  F = FlatIndex();
+  F.n_shards = n_shards;
+  F.idf_weighting = 0.0;                                  // unknown: idf values come from the files
+  PrebuiltInfo pi;
+
+  // 1. item dictionary: dense index = rank of the external id
+  std::vector<uint32_t> by_key(I); std::iota(by_key.begin(), by_key.end(), 0u);
+  std::sort(by_key.begin(), by_key.end(), [&](uint32_t a, uint32_t b) { return p.item_ids[a] < p.item_ids[b]; });
+  F.item_key.resize(I); F.idf.resize(I); F.attr.resize(I);
+  for (size_t d = 0; d < I; ++d) {
+    F.item_key[d] = p.item_ids[by_key[d]]; F.idf[d] = p.idf[by_key[d]]; F.attr[d] = p.attr[by_key[d]];
+    if (d > 0 && F.item_key[d] == F.item_key[d - 1]) { *err = "duplicate item id " + std::to_string(F.item_key[d]); return false; }
+  }
+  size_t cap = 16; while (cap < I * 2) cap <<= 1;
+  F.item_hash.assign(cap, ItemHashEntry{0, kEmpty, 0});
+  for (size_t d = 0; d < I; ++d) {
+    uint32_t h = (uint32_t)mix64(F.item_key[d]) & (uint32_t)(cap - 1);
+    while (F.item_hash[h].val != kEmpty) h = (h + 1) & (uint32_t)(cap - 1);
+    F.item_hash[h] = ItemHashEntry{F.item_key[d], (uint32_t)d, 0};
+  }
+
+  // 2. sessions named by at least one posting list are kept and ranked by (timestamp, session idx) ascending
+  std::vector<uint8_t> used(S, 0);
+  for (uint32_t sid : p.post_sessions) {
+    if (sid >= S || s.off[sid + 1] == s.off[sid]) {
+      *err = "a posting list names session " + std::to_string(sid) + ", which has no sessionindex record (the reference panics at mod.rs:138)";
+      return false;
+    }
+    used[sid] = 1;
+  }
+  std::vector<uint64_t> order;
+  for (size_t i = 0; i < S; ++i) if (used[i]) order.push_back(((uint64_t)s.ts[i] << 32) | (uint64_t)i);
+  std::sort(order.begin(), order.end());
+  const size_t Sk = order.size();
+  F.rank_to_orig.resize(Sk);
+  std::vector<uint32_t> rank_of(S, kEmpty);
+  for (size_t r = 0; r < Sk; ++r) { F.rank_to_orig[r] = (uint32_t)(order[r] & 0xFFFFFFFFull); rank_of[F.rank_to_orig[r]] = (uint32_t)r; }
+
+  // 3. session -> items (dense, ascending), 16-byte aligned starts
+  F.sess_ref.resize(Sk);
+  uint64_t P = 0; uint32_t max_len = 0;
+  std::vector<uint32_t> tmp;
+  for (size_t r = 0; r < Sk; ++r) {
+    const uint32_t o = F.rank_to_orig[r];
+    const uint32_t len = (uint32_t)(s.off[o + 1] - s.off[o]);
+    tmp.resize(len);
+    for (uint32_t t = 0; t < len; ++t) {
+      tmp[t] = host_lookup_item(F, s.items[s.off[o] + t]);
+      if (tmp[t] == kEmpty) {
+        *err = "session " + std::to_string(o) + " holds item " + std::to_string(s.items[s.off[o] + t]) +
+               ", which has no itemindex record (the reference panics at vmis_index.rs:322)";
+        return false;
+      }
+    }
+    std::sort(tmp.begin(), tmp.end());
+    for (uint32_t t = 1; t < len; ++t) if (tmp[t] == tmp[t - 1]) { *err = "duplicate item inside session " + std::to_string(o); return false; }
+    const size_t start = F.sess_items.size();
+    if ((start >> 2) > 0xFFFFFFFFull) { *err = "session item array too large"; return false; }
+    F.sess_ref[r] = make_uint2((uint32_t)(start >> 2), len);
+    F.sess_items.insert(F.sess_items.end(), tmp.begin(), tmp.end());
+    while (F.sess_items.size() & 3) F.sess_items.push_back(kEmpty);
+    P += len; max_len = std::max(max_len, len);
+  }
+  F.n_pairs_kept = P; F.max_len = max_len;
+
+  // 4. postings as time ranks, descending; lists in another order (or with repeats) are normalised
+  F.post_ref.resize(I);
+  std::vector<uint64_t> shard_size(n_shards, 0);
+  std::vector<std::vector<uint32_t>> lists(I);
+  uint32_t m_build = 0;
+  for (size_t d = 0; d < I; ++d) {
+    const uint32_t src = by_key[d];
+    std::vector<uint32_t>& L = lists[d];
+    L.reserve(p.post_off[src + 1] - p.post_off[src]);
+    bool sorted = true;
+    for (uint64_t e = p.post_off[src]; e < p.post_off[src + 1]; ++e) {
+      const uint32_t r = rank_of[p.post_sessions[e]];
+      const uint2 ref = F.sess_ref[r];
+      const uint32_t* it = &F.sess_items[(size_t)ref.x * 4];
+      if (!std::binary_search(it, it + ref.y, (uint32_t)d)) {
+        *err = "the posting list of item " + std::to_string(F.item_key[d]) + " names session " + std::to_string(p.post_sessions[e]) +
+               ", which does not contain the item";
+        return false;
+      }
+      if (!L.empty() && r >= L.back()) sorted = false;
+      L.push_back(r);
+    }
+    if (!sorted) {
+      ++pi.lists_reordered;
+      std::sort(L.begin(), L.end(), [](uint32_t a, uint32_t b) { return a > b; });
+      const size_t before = L.size();
+      L.erase(std::unique(L.begin(), L.end()), L.end());
+      pi.duplicate_postings += before - L.size();
+    }
+    const uint32_t len = (uint32_t)L.size();
+    m_build = std::max(m_build, len);
+    uint64_t& sz = shard_size[d % n_shards];
+    if ((sz >> 2) > 0xFFFFFFFFull) { *err = "posting array too large"; return false; }
+    F.post_ref[d] = make_uint2((uint32_t)(sz >> 2), len);
+    F.n_postings += len;
+    sz += (len + 3u) & ~3u;
+  }
+  F.m_build = std::max(m_build, 1u);
+  F.shard_begin.assign(n_shards + 1, 0);
+  for (uint32_t sh = 0; sh < n_shards; ++sh) F.shard_begin[sh + 1] = F.shard_begin[sh] + shard_size[sh];
+  F.postings.assign(F.shard_begin[n_shards], kEmpty);
+  for (size_t d = 0; d < I; ++d)
+    std::copy(lists[d].begin(), lists[d].end(), F.postings.begin() + F.shard_begin[d % n_shards] + (size_t)F.post_ref[d].x * 4);
+
+  // 5. m_carry: the kernel may take the first-match position of mod.rs:133-138 from the merged lists only if a
+  //    session of the m-sample is on the list of every evolving item it contains.  That holds for m <= the
+  //    shortest list that (a) misses some session containing its item and (b) is the most-recent prefix of them.
+  uint32_t m_carry = 0xFFFFFFFFu;
+  {
+    std::vector<uint32_t> newer_or_listed(I, 0), df(I, 0);
+    for (size_t r = 0; r < Sk; ++r) {
+      const uint2 ref = F.sess_ref[r];
+      const uint32_t* it = &F.sess_items[(size_t)ref.x * 4];
+      for (uint32_t t = 0; t < ref.y; ++t) {
+        const uint32_t d = it[t];
+        ++df[d];
+        if (!lists[d].empty() && (uint32_t)r >= lists[d].back()) ++newer_or_listed[d];
+      }
+    }
+    for (size_t d = 0; d < I; ++d) {
+      const uint32_t len = (uint32_t)lists[d].size();
+      if (len == df[d]) continue;                                  // complete list
+      if (newer_or_listed[d] != len) { m_carry = 0; break; }       // not a most-recent prefix
+      m_carry = std::min(m_carry, len);
+    }
+  }
+  pi.m_carry = m_carry;
+  F.m_carry = m_carry;
+  if (info) *info = pi;
   return true;
 }
 

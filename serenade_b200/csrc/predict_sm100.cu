@@ -515,10 +515,11 @@ vmis_predict_kernel(const IndexView ix, const PredictArgs a, const LaunchPlan pl
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const uint32_t K = a.k, M = a.m, N = a.how_many;
   const bool neighbors_mode = a.out_sess != nullptr;
-  // With m <= m_build a session of the m-sample is on the (truncated) posting list of EVERY evolving item it
-  // contains, so the first-match position of mod.rs:133-138 is the position of the first list it came from.
-  // Otherwise the item lists are scanned as the reference does.
-  const bool pos_from_lists = M <= ix.m_build;
+  // With m <= m_carry (= m_build for an index built here; checked at load for a pre-computed one) a session of
+  // the m-sample is on the (truncated) posting list of EVERY evolving item it contains, so the first-match
+  // position of mod.rs:133-138 is the position of the first list it came from.  Otherwise the item lists are
+  // scanned as the reference does.
+  const bool pos_from_lists = M <= ix.m_carry;
   uint32_t par = 0;                                                // scan scratch parity (block-uniform)
   uint32_t bar_parity = 0;                                         // bit b: phase parity of S.bar[b]
   if (tid == 0) {

@@ -57,7 +57,8 @@ struct IndexView {
   const uint32_t* rank_to_orig;
   uint32_t n_items;
   uint32_t n_kept;
-  uint32_t m_build;
+  uint32_t m_build;           // longest posting list (staging capacity)
+  uint32_t m_carry;           // m <= m_carry: every session of the m-sample is on the list of each evolving item it holds
   uint32_t max_len;
 };
 

@@ -36,6 +36,7 @@ struct FlatIndex {
   uint64_t n_pairs_kept = 0;
   uint64_t n_postings = 0;
   uint32_t m_build = 0;
+  uint32_t m_carry = 0;                    // largest m for which first-match positions come from the merged lists
   uint32_t max_len = 0;
   double idf_weighting = 0;
 };

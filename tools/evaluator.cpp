@@ -3,6 +3,7 @@
 // ONE batched predict call, and prints qty evaluations, Mrr@20 and HitRate@20 (metrics/mrr.rs, metrics/hitrate.rs).
 //   usage: evaluator train.txt test.txt [m=500] [k=50] [how_many=21] [max_items_in_session=2] [idf_weighting=1]
 // With --kat it runs the reference's known-answer test should_train_and_predict (mod.rs:229-310) instead.
+#include <sys/stat.h>
 #include <algorithm>
 #include <chrono>
 #include <cmath>
@@ -31,7 +32,10 @@ int main(int argc, char** argv) {
     const size_t m = argc > 3 ? std::strtoull(argv[3], nullptr, 10) : 500, k = argc > 4 ? std::strtoull(argv[4], nullptr, 10) : 50;
     const size_t how_many = argc > 5 ? std::strtoull(argv[5], nullptr, 10) : 21, max_items = argc > 6 ? std::strtoull(argv[6], nullptr, 10) : 2;
     const double idf_w = argc > 7 ? std::strtod(argv[7], nullptr) : 1.0;
-    auto index = vmis::VMISIndex::new_from_csv(argv[1], m, idf_w);
+    // evaluator.rs:19-35: a directory is the offline-computed Avro index, a file is a training TSV
+    struct stat st{};
+    if (stat(argv[1], &st) != 0) { std::fprintf(stderr, "Training data file does not exist: %s\n", argv[1]); return 2; }
+    auto index = S_ISDIR(st.st_mode) ? vmis::VMISIndex::new_(argv[1]) : vmis::VMISIndex::new_from_csv(argv[1], m, idf_w);
     // io.rs:40-59 read_test_data_evolving
     std::map<uint64_t, std::vector<std::pair<uint64_t, uint64_t>>> by_session;
     FILE* f = std::fopen(argv[2], "rb");
