@@ -233,6 +233,31 @@ void vmis_batcher_destroy(vmis_batcher_t* batcher);
 
 /* ---- misc ---------------------------------------------------------------- */
 
+/* ---- serving shell: GET /v1/recommend minus HTTP (recommend_resource.rs:20-65) ------------------------------
+ * Evolving-session window over an in-process store with the semantics of RocksDBSessionStore (sessions/mod.rs:
+ * key md5(session_id) as u128, sessions idle for more than max_session_idle_secs (default 20 min) start over,
+ * entries older than session_ttl_secs (default 30 min, serving.rs:55-56) are dropped), then predict through a
+ * micro-batcher.  Thread safe; call vmis_server_recommend from every worker thread. */
+typedef struct vmis_server vmis_server_t;
+vmis_server_t* vmis_server_create(const vmis_index_t* index, uint32_t k, uint32_t m, uint32_t how_many,
+                                  uint32_t max_items_in_session, int enable_business_logic, uint32_t max_batch,
+                                  uint32_t max_wait_us, uint64_t session_ttl_secs, uint64_t max_session_idle_secs);
+/* v1_recommend: updates the session (user_consent != 0) or uses [item_id] alone, predicts, writes up to how_many
+ * item ids best first (scores optional).  Returns the count or a negative VMIS_ERR_*. */
+int vmis_server_recommend(vmis_server_t* server, const char* session_id, uint64_t item_id, int user_consent,
+                          uint64_t* out_ids, double* out_scores_or_null);
+/* The window step alone (recommend_resource.rs:39-54): returns the evolving session that would be predicted on. */
+int vmis_server_session_window(vmis_server_t* server, const char* session_id, uint64_t item_id, int user_consent,
+                               uint64_t* out_items, size_t cap);
+/* get_session_items (sessions/mod.rs:37-57) without modifying the store. */
+int vmis_server_stored_items(vmis_server_t* server, const char* session_id, uint64_t* out_items, size_t cap);
+/* Tests: pin the store's clock to epoch_secs (0 = system clock again) and sweep expired entries. */
+int vmis_server_set_clock(vmis_server_t* server, uint64_t epoch_secs);
+int vmis_server_stats(vmis_server_t* server, uint64_t* n_sessions, uint64_t* n_batches, uint64_t* n_requests);
+void vmis_server_destroy(vmis_server_t* server);
+/* md5 digest used for the session key (recommend_resource.rs:27). */
+void vmis_md5(const void* data, size_t len, uint8_t out16[16]);
+
 const char* vmis_last_error(void);   /* message of the last failure on this thread */
 int vmis_last_error_code(void);      /* its VMIS_ERR_* code (constructors return NULL on failure) */
 const char* vmis_version(void);

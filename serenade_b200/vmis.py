@@ -87,6 +87,14 @@ def load_library():
         "vmis_batcher_predict": (i32, [vp, _u64p, sz, _u64p, _f64p]),
         "vmis_batcher_stats": (i32, [vp, _u64p, _u64p]),
         "vmis_batcher_destroy": (None, [vp]),
+        "vmis_server_create": (vp, [vp, u32, u32, u32, u32, i32, u32, u32, u64, u64]),
+        "vmis_server_recommend": (i32, [vp, C.c_char_p, u64, i32, _u64p, _f64p]),
+        "vmis_server_session_window": (i32, [vp, C.c_char_p, u64, i32, _u64p, sz]),
+        "vmis_server_stored_items": (i32, [vp, C.c_char_p, _u64p, sz]),
+        "vmis_server_set_clock": (i32, [vp, u64]),
+        "vmis_server_stats": (i32, [vp, _u64p, _u64p, _u64p]),
+        "vmis_server_destroy": (None, [vp]),
+        "vmis_md5": (None, [C.c_char_p, sz, _u8p]),
         "vmis_last_error": (C.c_char_p, []),
         "vmis_last_error_code": (i32, []),
         "vmis_version": (C.c_char_p, []),
@@ -107,7 +115,9 @@ EXPORTED_SYMBOLS = ("vmis_index_from_csv", "vmis_index_from_csv_ex", "vmis_index
                     "vmis_predict_batch_device", "vmis_predict", "vmis_find_neighbors_batch", "vmis_items_for_session",
                     "vmis_idf", "vmis_find_attributes", "vmis_postings", "vmis_session_timestamp",
                     "vmis_synth_sessions", "vmis_synth_queries", "vmis_batcher_create", "vmis_batcher_predict",
-                    "vmis_batcher_stats", "vmis_batcher_destroy", "vmis_last_error", "vmis_last_error_code",
+                    "vmis_batcher_stats", "vmis_batcher_destroy", "vmis_server_create", "vmis_server_recommend",
+                    "vmis_server_session_window", "vmis_server_stored_items", "vmis_server_set_clock", "vmis_server_stats",
+                    "vmis_server_destroy", "vmis_md5", "vmis_last_error", "vmis_last_error_code",
                     "vmis_version")
 
 
@@ -400,3 +410,58 @@ class Batcher:
         self._b = None
 
     __del__ = close
+
+
+class Server:
+    """``GET /v1/recommend`` without the HTTP layer (recommend_resource.rs:20-65): evolving-session window over an
+    in-process store with RocksDBSessionStore semantics (sessions/mod.rs), then ``predict`` through a micro-batcher."""
+
+    def __init__(self, index, k, m, how_many, max_items_in_session, enable_business_logic=False, max_batch=4096,
+                 max_wait_us=200, session_ttl_secs=30 * 60, max_session_idle_secs=20 * 60):
+        self._index = index
+        self._how_many = how_many
+        self._cap = max(max_items_in_session, 1)
+        self._s = C.c_void_p(load_library().vmis_server_create(index.handle, k, m, how_many, max_items_in_session,
+                                                              int(enable_business_logic), max_batch, max_wait_us,
+                                                              session_ttl_secs, max_session_idle_secs))
+        if not self._s:
+            raise VmisError(-1, "vmis_server_create failed")
+
+    def recommend(self, session_id, item_id, user_consent=True):
+        """v1_recommend → list of item ids, best first"""
+        ids = np.zeros(max(self._how_many, 1), dtype=np.uint64)
+        n = _check(load_library().vmis_server_recommend(self._s, session_id.encode(), int(item_id), int(user_consent),
+                                                        _p(ids, C.c_uint64), None))
+        return [int(x) for x in ids[:n]]
+
+    def session_window(self, session_id, item_id, user_consent=True):
+        buf = np.zeros(self._cap + 1, dtype=np.uint64)
+        n = _check(load_library().vmis_server_session_window(self._s, session_id.encode(), int(item_id), int(user_consent),
+                                                             _p(buf, C.c_uint64), len(buf)))
+        return [int(x) for x in buf[:n]]
+
+    def stored_items(self, session_id):
+        buf = np.zeros(self._cap + 1, dtype=np.uint64)
+        n = _check(load_library().vmis_server_stored_items(self._s, session_id.encode(), _p(buf, C.c_uint64), len(buf)))
+        return [int(x) for x in buf[:n]]
+
+    def set_clock(self, epoch_secs):
+        _check(load_library().vmis_server_set_clock(self._s, int(epoch_secs)))
+
+    def stats(self):
+        a, b, c = C.c_uint64(), C.c_uint64(), C.c_uint64()
+        _check(load_library().vmis_server_stats(self._s, C.byref(a), C.byref(b), C.byref(c)))
+        return {"sessions": a.value, "batches": b.value, "requests": c.value}
+
+    def close(self):
+        if getattr(self, "_s", None) and _lib is not None:
+            _lib.vmis_server_destroy(self._s)
+        self._s = None
+
+    __del__ = close
+
+
+def md5(data):
+    out = np.zeros(16, dtype=np.uint8)
+    load_library().vmis_md5(data, len(data), _p(out, C.c_uint8))
+    return bytes(out)

@@ -381,3 +381,36 @@ def test_micro_batcher_online_shape(sb, toy):
     assert st["requests"] == len(queries) and st["batches"] < len(queries)      # requests really were coalesced
     assert b.predict([]) == []
     b.close()
+
+
+def test_serving_shell_recommend(sb, toy):
+    """GET /v1/recommend minus HTTP: the README request (README.md:131-155) and concurrent visitors whose evolving
+    sessions grow request by request (recommend_resource.rs:39-64) — every answer equals predict() on the window"""
+    import threading
+    gix, oix, tests = toy
+    srv = sb.Server(gix, 288, 1502, 21, max_items_in_session=4, max_batch=64, max_wait_us=300)
+    ids = srv.recommend("144", 13598, user_consent=True)
+    assert sorted(ids) == sorted(README_13598) and ids[:3] == README_13598[:3]
+    sessions = [tests[s] for s in sorted(tests)][:64]
+    errs = []
+
+    def visitor(v):
+        try:
+            window = []
+            for item in sessions[v]:
+                if not window:
+                    window = [item]
+                elif window[-1] != item:
+                    window = (window + [item])[-4:]
+                got = srv.recommend("visitor-%d" % v, item)
+                want = [r[0] for r in sb.predict(gix, window, 288, 1502, 21)]
+                assert got == want, (v, window)
+        except Exception as e:  # noqa: BLE001
+            errs.append(e)
+
+    th = [threading.Thread(target=visitor, args=(v,)) for v in range(len(sessions))]
+    [x.start() for x in th]
+    [x.join() for x in th]
+    assert not errs, errs[:2]
+    assert srv.recommend("nobody", 13598, user_consent=False) == ids
+    srv.close()
