@@ -220,9 +220,8 @@ __device__ __forceinline__ int32_t session_weight10(uint32_t low) {
 // The neighbours' item lists are walked as ONE flat array of `total` entries, 32 consecutive entries per warp
 // round, so every lane always has exactly one item.  The entry → neighbour map costs two broadcast loads: a
 // bitmap of list starts (fbits) and, per 32-entry word, the neighbour that owns its first entry (fdir); the
-// lane's neighbour is fdir + popcount of the starts up to its bit.  Inserts run as a warp-converged linear
-// probing loop (one probe step of every unfinished lane per iteration); the next round's gathers are issued
-// before the loop.  The occupied slots are compacted afterwards (compact_slots) for phase 3.
+// lane's neighbour is fdir + popcount of the starts up to its bit.  Inserts use double hashing with persistent
+// lanes (see accumulate()).
 // The most recent item of the evolving session is never inserted: it is dropped from the result anyway
 // (mod.rs:157-160) and would be the hottest slot of the table.
 struct FlatMap {
@@ -232,64 +231,77 @@ struct FlatMap {
   const uint32_t* w;        // [nn]    weight 10*linear_score*numerator
 };
 
-constexpr uint32_t kMaxProbe = 512;        // a probe sequence this long means the table is (nearly) full
-
 // Returns the number of slots this WARP claimed; when kRecord, their indices are appended to the warp's own
 // segment `occ_seg` (phase 3 lets every warp score the slots it claimed, so no compaction pass is needed).
+//
+// Lanes are PERSISTENT: every warp owns a contiguous share of the flat entry array; a lane whose insert has
+// finished takes its prefetched next entry and prefetches another one (entries are dealt to the free lanes by
+// a ballot rank), a lane whose probe hit a foreign key just steps on.  Each loop iteration is therefore one
+// probe step of (nearly) 32 live inserts — a round-synchronous loop would idle ~27 lanes while the slowest
+// insert of the round walks its probe sequence (measured: 3.1 iterations per 32 entries at 5 live lanes).
 template <bool kRecord>
 __device__ __forceinline__ uint32_t accumulate(const IndexView& ix, SmemLayout& S, const FlatMap fm, uint32_t total,
                                                uint32_t last_idx, uint32_t* keys, int32_t* vals, uint32_t mask,
                                                uint16_t* occ_seg, uint32_t seg_cap) {
   const uint32_t lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
-  const uint32_t lt_mask = (1u << lane) - 1u, le_mask = 0xFFFFFFFFu >> (31u - lane);
-  auto gather = [&](uint32_t base, uint32_t& item, int32_t& wgt) {
+  const uint32_t lt_mask = (1u << lane) - 1u;
+  const uint32_t n32 = (total + 31u) >> 5;
+  uint32_t cur_e = ((n32 * warp) / kWarps) << 5;                       // next entry of this warp's share to deal out
+  const uint32_t end_e = min(((n32 * (warp + 1u)) / kWarps) << 5, total);
+  auto gather = [&](uint32_t e, uint32_t& item, int32_t& wgt) {
     item = kEmpty; wgt = 0;
-    const uint32_t e = base + lane;
-    if (e < total) {
-      const uint32_t word = base >> 5, b = fm.bits[word];
-      const uint32_t i = (uint32_t)fm.dir[word] + (uint32_t)__popc(b & le_mask) - (b & 1u);
+    if (e < end_e) {
+      const uint32_t word = e >> 5, b = fm.bits[word];
+      const uint32_t i = (uint32_t)fm.dir[word] + (uint32_t)__popc(b & (0xFFFFFFFFu >> (31u - (e & 31u)))) - (b & 1u);
       item = __ldg(ix.sess_items + (fm.delta[i] + e));
       wgt = (int32_t)fm.w[i];
-      if (item == last_idx) item = kEmpty;
     }
   };
   uint32_t wn = 0;                                   // warp-uniform count of claimed slots
-  uint32_t nxt_item = kEmpty; int32_t nxt_w = 0;
-  uint32_t base = warp * 32;
-  if (base < total) gather(base, nxt_item, nxt_w);
-  for (; base < total; base += kThreads) {
-    const uint32_t idx = nxt_item;
-    const int32_t w = nxt_w;
-    if (base + kThreads < total) gather(base + kThreads, nxt_item, nxt_w);
-    bool done = idx == kEmpty;
-    // double hashing: an odd stride visits every slot of the power-of-two table and avoids the primary
-    // clustering of linear probing (shared memory has no locality to lose)
-    const uint32_t hv = idx * 0x9E3779B1u;
-    const uint32_t stride = ((hv >> 20) | 1u) & mask;
-    uint32_t h = (hv >> 7) & mask;
-    bool claimed = false;                            // a lane claims at most one slot per round (its item's)
-    for (uint32_t steps = 0;; ++steps) {             // warp-converged: one probe step of every unfinished lane
-      if (!done) {
-        uint32_t cur = *reinterpret_cast<volatile uint32_t*>(&keys[h]);
-        if (cur == kEmpty) {
-          cur = atomicCAS(&keys[h], kEmpty, idx);
-          if (cur == kEmpty) { claimed = true; cur = idx; }
-        }
-        if (cur == idx) { atomicAdd(&vals[h], w); done = true; }
-      }
-      if (!__any_sync(kFull, !done)) break;
-      if (steps >= kMaxProbe) { S.overflow = 1u; break; }
-      if (!done) h = (h + stride) & mask;
+  uint32_t item = kEmpty, h = 0, stride = 0; int32_t w = 0;
+  uint32_t nitem; int32_t nw;                        // prefetched entry of the lane (not looked at until promoted)
+  gather(cur_e + lane, nitem, nw);
+  cur_e += 32u;
+  bool done = true;
+  const uint32_t seg_last = seg_cap - 1u;
+  for (uint32_t budget = total + 8192u; budget != 0u; --budget) {     // the budget is unreachable while the table has free slots
+    const uint32_t dm = __ballot_sync(kFull, done);
+    if (done) {
+      item = nitem; w = nw;
+      if (item == last_idx) item = kEmpty;           // dropped from the result anyway (mod.rs:157-160)
+      // double hashing: an odd stride visits every slot of the power-of-two table and avoids the primary
+      // clustering of linear probing (shared memory has no locality to lose)
+      const uint32_t hv = item * 0x9E3779B1u;
+      stride = ((hv >> 20) | 1u) & mask;
+      h = (hv >> 7) & mask;
+      done = item == kEmpty;
+      gather(cur_e + (uint32_t)__popc(dm & lt_mask), nitem, nw);
     }
-    if (kRecord) {                                   // h still addresses the slot the lane landed on
-      const uint32_t cm = __ballot_sync(kFull, claimed);
-      if (claimed) {
-        const uint32_t n = wn + (uint32_t)__popc(cm & lt_mask);
-        if (n < seg_cap) occ_seg[n] = (uint16_t)h; else S.overflow = 1u;
+    cur_e += (uint32_t)__popc(dm);
+    if (dm == kFull && !__any_sync(kFull, !done)) {                    // every lane was idle and none got a live entry
+      if (!__any_sync(kFull, nitem != kEmpty)) break;                  // ... and nothing is prefetched: finished
+      continue;
+    }
+    bool claimed = false;
+    if (!done) {
+      uint32_t cur = *reinterpret_cast<volatile uint32_t*>(&keys[h]);
+      if (cur == kEmpty) {
+        cur = atomicCAS(&keys[h], kEmpty, item);
+        if (cur == kEmpty) { claimed = true; cur = item; }
       }
-      wn += (uint32_t)__popc(cm);
+      if (cur == item) { atomicAdd(&vals[h], w); done = true; }
+      else h = (h + stride) & mask;
+    }
+    if (kRecord) {
+      const uint32_t cm = __ballot_sync(kFull, claimed);
+      if (cm) {                                      // h still addresses the slot the lane landed on
+        if (claimed) occ_seg[min(wn + (uint32_t)__popc(cm & lt_mask), seg_last)] = (uint16_t)h;
+        wn += (uint32_t)__popc(cm);
+        if (wn > seg_cap) break;                     // over budget: the query is redone on the global table
+      }
     }
   }
+  if (kRecord && wn > seg_cap) S.overflow = 1u;
   return min(wn, seg_cap);
 }
 
@@ -411,6 +423,8 @@ __device__ __forceinline__ uint32_t select_topn(const IndexView& ix, const Predi
           queue[lane] = rest;
           qn -= 32;
           __syncwarp();
+          // the warp's own N-th best so far is also a lower bound of the global N-th best: prune harder from here on
+          bound = max(bound, __shfl_sync(kFull, best, (int)N - 1) >> kIdxBits);
         }
       }
     }
