@@ -433,15 +433,28 @@ __device__ __forceinline__ uint32_t select_topn(const IndexView& ix, const Predi
     buf[warp * 32 + lane] = best;
     __syncthreads();
     if (warp == 0) {
-      best = buf[lane];
-      for (int w = 1; w < kWarps; ++w) best = u32_merge_top(best, buf[w * 32 + lane], lane);
+      // tree merge of the per-warp lists: the merges of one level are independent (shuffle latencies overlap)
+      uint32_t lists[kWarps];
+#pragma unroll
+      for (int w = 0; w < kWarps; ++w) lists[w] = buf[w * 32 + lane];
+#pragma unroll
+      for (int st = 1; st < kWarps; st <<= 1) {
+#pragma unroll
+        for (int w = 0; w + st < kWarps; w += 2 * st) lists[w] = u32_merge_top(lists[w], lists[w + st], lane);
+      }
+      best = lists[0];
       const uint32_t valid = __popc(__ballot_sync(kFull, best != 0));
       const uint32_t take = min(valid, N);
       bool ok = valid < 32;
       if (!ok) ok = (__shfl_sync(kFull, best, 31) >> kIdxBits) + 1u < (__shfl_sync(kFull, best, (int)N - 1) >> kIdxBits);
       if (ok) {
         Elem x; x.s = 0; x.id = kEmpty;
-        if (best != 0) { const uint32_t slot = occ[best & kIdxMask]; x = exact_elem(ix, a, c, keys[slot], vals[slot], denom); }
+        if (best != 0) {
+          const uint32_t slot = occ[best & kIdxMask], key = keys[slot];
+          // the external id is read after the sort: start pulling its line now
+          asm volatile("prefetch.global.L2 [%0];" ::"l"(ix.item_key + key));
+          x = exact_elem(ix, a, c, key, vals[slot], denom);
+        }
         x = warp_sort_desc(x, lane);
         if ((uint32_t)lane < take) {
           a.out_ids[(size_t)q * N + lane] = ix.item_key[x.id];
