@@ -15,13 +15,16 @@
 //            search for the threshold numerator, one ordered scan for the ties (vmis_index.rs:394-412)
 //   phase 2a neighbour directory: item-list refs, integer weight 10·linear_score·numerator
 //            (mod.rs:133-142, :110-116), flat entry → neighbour map (bitmap + word directory)
-//   phase 2b A[item] += weight for every item of every neighbour (mod.rs:144-153): one item per lane,
-//            warp-converged double-hashing inserts into a 4096-slot shared table; every warp keeps the
-//            list of slots it claimed; rare overflow → the CTA's global table
+//   phase 2b A[item] += weight for every item of every neighbour (mod.rs:144-153): persistent lanes —
+//            a lane whose insert finished takes the next flat entry (dealt by ballot rank, prefetched a
+//            trip ahead), a lane that hit a foreign key steps on; double-hashing inserts into a 4096-slot
+//            shared table; every warp keeps the list of slots it claimed; rare overflow → the CTA's
+//            global table
 //   phase 3  drop the current item (mod.rs:157-160), business rules (:162-182), top-n by (score desc,
 //            item id asc) (mod.rs:185-214): fp32 coarse keys through a u32 warp-bitonic network with a
-//            shared lower bound, the 32 survivors rescored exactly (f64 g(idf)·A/(10·u)) and sorted once;
-//            a margin test proves the survivors contain the exact top-n, else an exact 96-bit network runs
+//            shared lower bound (tightened per warp by its running n-th best), per-warp lists merged as
+//            a tree, the 32 survivors rescored exactly (f64 g(idf)·A/(10·u)) and sorted once; a margin
+//            test proves the survivors contain the exact top-n, else an exact 96-bit network runs
 //
 // All session/item arithmetic is integer and order independent; the only floating point that reaches the
 // output is one f64 multiply + divide per final candidate, so results are bit-exact against the canonical mode
