@@ -107,3 +107,21 @@ def test_prebuilt_save_load_keeps_m_carry(sb, oracle, tmp_path):
     b = sb.predict_batch(gl, qs, 9, 16, 21)
     for x, y in zip(a, b):
         assert np.array_equal(x, y)
+
+
+def test_avro_index_item_sharded(sb, oracle, tmp_path):
+    """the Avro index with its posting lists split by item over 3 handles (peers attached by pointer): same answers"""
+    rng = np.random.default_rng(79)
+    items, off, ts = random_index_data(rng, 600, 60, max_len=7, id_scale=13)
+    src = oracle.OracleIndex.from_sessions(items, off, ts, 25, 7, 2.0)
+    parts = au.parts_from_oracle(src, items, off, ts)
+    au.write_index_dir(str(tmp_path), parts, style="spark", codec="deflate", files=2)
+    shards = [sb.VMISIndex.new(str(tmp_path), device=0, shard=s, n_shards=3) for s in range(3)]
+    for a in range(3):
+        for b in range(3):
+            if a != b:
+                shards[a].attach_shard_ptr(b, shards[b].shard_ptr())
+    oix = _oracle_from_parts(oracle, parts)
+    qs = _queries(rng, np.unique(items), 200)
+    for sh in shards:
+        _equal(sb, sh, oix, qs, 20, 25, 21)
