@@ -350,7 +350,8 @@ bool snappy_uncompress(const uint8_t* s, size_t n, std::vector<uint8_t>* out, st
     const uint8_t b = *s++; len |= (uint64_t)(b & 0x7F) << shift; shift += 7;
     if (!(b & 0x80)) break;
   }
-  if (len > (uint64_t(1) << 32)) { *err = "corrupt snappy block (length)"; return false; }
+  // a copy element is at least 2 bytes and yields at most 64: a valid stream cannot expand more than 32 x
+  if (len > (uint64_t(1) << 32) || len > (uint64_t)n * 32 + 64) { *err = "corrupt snappy block (length)"; return false; }
   out->resize(len);
   uint8_t* d = out->data(); uint8_t* const d0 = d; uint8_t* const de = d + len;
   auto bad = [&]() { *err = "corrupt snappy block"; return false; };

@@ -26,6 +26,7 @@ thread_local int g_err_code = 0;
 int fail(int code, const char* fmt, ...) {
   char buf[512];
   va_list ap; va_start(ap, fmt); vsnprintf(buf, sizeof buf, fmt, ap); va_end(ap);
+  for (char* c = buf; *c; ++c) if ((unsigned char)*c < 0x20 || (unsigned char)*c > 0x7E) *c = '?';   // messages may quote file content
   g_err = buf;
   g_err_code = code;
   return code;

@@ -123,7 +123,7 @@ EXPORTED_SYMBOLS = ("vmis_index_from_csv", "vmis_index_from_csv_ex", "vmis_index
 
 def _check(rc):
     if rc < 0:
-        raise VmisError(rc, load_library().vmis_last_error().decode())
+        raise VmisError(rc, load_library().vmis_last_error().decode(errors="replace"))
     return rc
 
 
@@ -145,7 +145,7 @@ class VMISIndex:
 
     def __init__(self, handle):
         if not handle:
-            raise VmisError(load_library().vmis_last_error_code(), load_library().vmis_last_error().decode())
+            raise VmisError(load_library().vmis_last_error_code(), load_library().vmis_last_error().decode(errors="replace"))
         self._h = C.c_void_p(handle)
 
     # -- constructors -------------------------------------------------------------------------------

@@ -252,3 +252,37 @@ def test_snappy_decoder_copy_elements(sb, tmp_path):
         assert gix.session_timestamp(s) == 100 + s
     np.testing.assert_array_equal(gix.postings(2001), list(range(39, 0, -2)))
     assert gix.prebuilt_info()["lists_reordered"] == 0
+
+
+def test_avro_loader_survives_corruption(sb, oracle, tmp_path):
+    """byte flips, truncations and insertions anywhere in a container: the loader either loads or fails with a
+    VmisError — it never crashes and never hangs"""
+    import random
+    rng = np.random.default_rng(12)
+    oix, parts = _parts(oracle, rng, n_sessions=120, n_items=30)
+    random.seed(3)
+    outcomes = {"ok": 0, "err": 0}
+    for codec, style in [("null", "spark"), ("deflate", "plain"), ("snappy", "spark")]:
+        base = tmp_path / codec
+        au.write_index_dir(str(base), parts, style=style, codec=codec, files=1, records_per_block=40)
+        for sub in ("itemindex", "sessionindex"):
+            f = base / sub / "part-00000.avro"
+            good = f.read_bytes()
+            for it in range(40):
+                b = bytearray(good)
+                if it % 3 == 0:
+                    for _ in range(random.randint(1, 4)):
+                        b[random.randrange(len(b))] = random.randrange(256)
+                elif it % 3 == 1:
+                    b = b[:random.randrange(1, len(b))]
+                else:
+                    pos = random.randrange(len(b))
+                    b[pos:pos] = bytes(random.randrange(256) for _ in range(random.randint(1, 9)))
+                f.write_bytes(bytes(b))
+                try:
+                    sb.VMISIndex.new(str(base), device=sb.DEVICE_NONE).close()
+                    outcomes["ok"] += 1
+                except sb.VmisError:
+                    outcomes["err"] += 1
+            f.write_bytes(good)
+    assert outcomes["err"] > 150 and outcomes["ok"] + outcomes["err"] == 240
