@@ -236,6 +236,8 @@ int check_common(const vmis_index* ix, uint32_t k, uint32_t m, vmis::LaunchPlan*
     return fail(VMIS_ERR_CUDA, "host-only index (VMIS_DEVICE_NONE): queries need a B200; there is no CPU fallback");
   for (uint32_t s2 = 0; s2 < ix->view.n_shards; ++s2)
     if (!ix->view.post_shard[s2]) return fail(VMIS_ERR_ARG, "posting shard %u of %u is not attached", s2, ix->view.n_shards);
+  if (ix->view.n_kept >= 0x80000000u)     // the list merges compare time ranks as signed numbers (kEmpty sentinel = -1)
+    return fail(VMIS_ERR_LIMIT, "%u kept sessions; the kernel handles fewer than 2^31", ix->view.n_kept);
   const int rc = vmis::plan_launch(ix->view, k, m, ix->sm_count, plan);
   if (rc != VMIS_OK)
     return fail(rc, "k=%u / m=%u beyond kernel limits (k <= %u, m <= %u and shared memory)", k, m, vmis::kMaxK, vmis::kMaxM);

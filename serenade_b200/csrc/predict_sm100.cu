@@ -626,6 +626,7 @@ vmis_predict_kernel(const IndexView ix, const PredictArgs a, const LaunchPlan pl
         };
         if (tid == 0) { fence_async_proxy(); issue(1, 0); if (nd > 2) issue(2, 1); }
         for (uint32_t i = tid; i < n0; i += kThreads) acc[i] = ((uint64_t)P0[i] << 32) | low0;
+        if (tid == 0) acc[n0] = ~0ull;                                        // sentinel (see the merge steps)
         uint32_t na = n0;
         for (uint32_t j = 1; j < nd; ++j) {
           const uint32_t bsel = (j - 1) & 1u;
@@ -637,6 +638,7 @@ vmis_predict_kernel(const IndexView ix, const PredictArgs a, const LaunchPlan pl
           postings_visited += nb;
           mbar_wait(&S.bar[bsel], (bar_parity >> bsel) & 1u);
           bar_parity ^= 1u << bsel;
+          if (tid == 0) const_cast<uint32_t*>(lst)[nb] = kEmpty;              // sentinel behind the staged list
           __syncthreads();
           // merge-path fold: out ← first M distinct of acc ∪ B, numerators summed, first position kept
           const uint32_t T = na + nb;
@@ -650,38 +652,34 @@ vmis_predict_kernel(const IndexView ix, const PredictArgs a, const LaunchPlan pl
               if ((uint32_t)(acc[mid] >> 32) >= lst[d0 - 1 - mid]) lo = mid + 1; else hi = mid;
             }
             uint32_t ai = lo, bi = d0 - lo;
-            uint64_t r[kVT];
+            uint32_t rh[kVT], rl[kVT];                    // merged element s: session rank, pos|numerator
             uint32_t vmask = 0;
-            // heads of both runs and the key of the last consumed A element stay in registers: one shared-memory
-            // load per merged element
-            uint64_t av = ai < na ? acc[ai] : 0ull;
-            uint32_t bk = bi < nb ? lst[bi] : 0u;
+            // Heads of both runs and the key of the last consumed A element stay in registers: one shared-memory
+            // load per merged element.  Both runs end in a kEmpty sentinel, which compares below every rank as a
+            // signed number, so the steps need no bounds checks.
+            uint64_t av = acc[ai];
+            uint32_t bk = lst[bi];
             uint32_t pak = ai > 0 ? (uint32_t)(acc[ai - 1] >> 32) : kEmpty;   // kEmpty is never a session rank
+            const uint32_t steps = d1 - d0;
 #pragma unroll
             for (int s = 0; s < kVT; ++s) {
-              r[s] = 0;
-              if (d0 + s < d1) {
-                const uint32_t ak = (uint32_t)(av >> 32);
-                const bool takeA = (ai < na) && (bi >= nb || ak >= bk);
-                if (takeA) {
-                  r[s] = av + ((bi < nb && bk == ak) ? cj : 0u);
-                  vmask |= 1u << s; pak = ak; ++ai;
-                  av = ai < na ? acc[ai] : 0ull;
-                } else {
-                  if (pak != bk) { r[s] = ((uint64_t)bk << 32) | lowj; vmask |= 1u << s; }
-                  ++bi;
-                  bk = bi < nb ? lst[bi] : 0u;
-                }
-              }
+              const uint32_t ak = (uint32_t)(av >> 32);
+              const bool takeA = (int32_t)ak >= (int32_t)bk;                  // equal ranks: A first, B is then a duplicate
+              const bool emit = (uint32_t)s < steps && (takeA || pak != bk);
+              rh[s] = takeA ? ak : bk;
+              rl[s] = takeA ? (uint32_t)av + (ak == bk ? cj : 0u) : lowj;
+              vmask |= (emit ? 1u : 0u) << s;
+              if (takeA) { pak = ak; ++ai; av = acc[ai]; } else { ++bi; bk = lst[bi]; }
             }
             int total;
             uint32_t p = out_count + (uint32_t)block_excl_scan(__popc(vmask), S.scan, par, total);
 #pragma unroll
             for (int s = 0; s < kVT; ++s) {
-              if ((vmask >> s) & 1u) { if (p < M) out[p] = r[s]; ++p; }
+              if ((vmask >> s) & 1u) { if (p < M) out[p] = ((uint64_t)rh[s] << 32) | rl[s]; ++p; }
             }
             out_count = min(M, out_count + (uint32_t)total);
           }
+          if (tid == 0) out[out_count] = ~0ull;                               // sentinel for the next fold
           __syncthreads();
           if (tid == 0 && j + 2 < nd) { fence_async_proxy(); issue(j + 2, bsel); }
           uint64_t* t = acc; acc = out; out = t;
@@ -894,8 +892,9 @@ uint32_t next_pow2(uint32_t x) { uint32_t p = 1; while (p < x) p <<= 1; return p
 int plan_launch(const IndexView& ix, uint32_t k, uint32_t m, int sm_count, LaunchPlan* plan) {
   if (k > kMaxK || m > kMaxM) return VMIS_ERR_LIMIT;
   LaunchPlan p{};
-  p.m_eff = (std::max(m, 1u) + 3u) & ~3u;
-  p.list_cap = (std::min(std::max(m, 1u), std::max(ix.m_build, 1u)) + 3u) & ~3u;
+  // one extra entry each: the merge steps read a sentinel behind both runs
+  p.m_eff = (std::max(m, 1u) + 1u + 3u) & ~3u;
+  p.list_cap = (std::min(std::max(m, 1u), std::max(ix.m_build, 1u)) + 1u + 3u) & ~3u;
   uint32_t tab = next_pow2(std::max(k, 1u) * 12u);
   p.tab_cap = std::min(std::max(tab, 1024u), 8192u);
   const size_t fixed = (sizeof(SmemLayout) + 15) & ~size_t(15);
