@@ -267,6 +267,7 @@ __device__ __forceinline__ uint32_t accumulate(const IndexView& ix, SmemLayout& 
   cur_e += 32u;
   bool done = true;
   const uint32_t seg_last = seg_cap - 1u;
+  bool finished = false;
   for (uint32_t budget = total + 8192u; budget != 0u; --budget) {     // the budget is unreachable while the table has free slots
     const uint32_t dm = __ballot_sync(kFull, done);
     if (done) {
@@ -282,7 +283,7 @@ __device__ __forceinline__ uint32_t accumulate(const IndexView& ix, SmemLayout& 
     }
     cur_e += (uint32_t)__popc(dm);
     if (dm == kFull && !__any_sync(kFull, !done)) {                    // every lane was idle and none got a live entry
-      if (!__any_sync(kFull, nitem != kEmpty)) break;                  // ... and nothing is prefetched: finished
+      if (!__any_sync(kFull, nitem != kEmpty)) { finished = true; break; }   // ... and nothing is prefetched
       continue;
     }
     bool claimed = false;
@@ -304,7 +305,7 @@ __device__ __forceinline__ uint32_t accumulate(const IndexView& ix, SmemLayout& 
       }
     }
   }
-  if (kRecord && wn > seg_cap) S.overflow = 1u;
+  if ((kRecord && wn > seg_cap) || !finished) S.overflow = 1u;           // over budget, or the probe guard ran out
   return min(wn, seg_cap);
 }
 
