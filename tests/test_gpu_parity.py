@@ -414,3 +414,16 @@ def test_serving_shell_recommend(sb, toy):
     assert not errs, errs[:2]
     assert srv.recommend("nobody", 13598, user_consent=False) == ids
     srv.close()
+
+
+def test_evaluator_line_all_eight_metrics(sb, toy, toy_dir):
+    """the line the reference's evaluator prints (README.md:170-171), from ONE batched predict through the kernel"""
+    from serenade_b200.evaluate import evaluate_all, read_test_sessions as rts, read_training_items
+    train = os.path.join(toy_dir, "train.txt")
+    gix = sb.VMISIndex.new_from_csv(train, 500, 1.0, max_len=15, device=0)
+    res = evaluate_all(gix, read_training_items(train), rts(os.path.join(toy_dir, "test.txt")), 50, 500, 21, 2, 20)
+    assert res["qty_evaluations"] == 931
+    want = {"Mrr@20": 0.3277, "Ndcg@20": 0.3553, "HitRate@20": 0.6402, "Popularity@20": 0.0499, "Precision@20": 0.0680,
+            "Coverage@20": 0.2765, "Recall@20": 0.4456, "F1score@20": 0.1180}
+    for name, v in want.items():
+        assert res[name] == pytest.approx(v, abs=0.004), (name, res[name], v)
