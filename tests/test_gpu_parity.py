@@ -351,8 +351,11 @@ def test_cpp_evaluator_tool(toy_dir, tmp_path):
                          capture_output=True, text=True)
     assert out.returncode == 0, out.stderr
     assert "Qty test evaluations: 931" in out.stdout
-    mrr, hr = [float(x) for x in out.stdout.split("Mrr@20,HitRate@20\n")[1].split("\n")[0].split(",")]
-    assert hr == pytest.approx(0.6402, abs=0.0006) and mrr == pytest.approx(0.3277, abs=0.004)
+    header = "Mrr@20,Ndcg@20,HitRate@20,Popularity@20,Precision@20,Coverage@20,Recall@20,F1score@20\n"   # README.md:170
+    got = [float(x) for x in out.stdout.split(header)[1].split("\n")[0].split(",")]
+    for g, w in zip(got, [0.3277, 0.3553, 0.6402, 0.0499, 0.0680, 0.2765, 0.4456, 0.1180]):          # README.md:171
+        assert g == pytest.approx(w, abs=0.004)
+    assert got[2] == pytest.approx(0.6402, abs=0.0006)
 
 
 def test_micro_batcher_online_shape(sb, toy):
