@@ -798,7 +798,15 @@ vmis_predict_kernel(const IndexView ix, const PredictArgs a, const LaunchPlan pl
     }
 
     // ------------------------------------------------------------------ phase 2a: neighbour directory
-    for (uint32_t i = tid; i < plan.tab_cap; i += kThreads) { stab_keys[i] = kEmpty; stab_vals[i] = 0; }
+    {
+      // keys and values are adjacent and the capacity is a multiple of 1024: clear both with 16-byte stores
+      uint4* t4 = reinterpret_cast<uint4*>(stab_keys);
+      const uint32_t n4 = plan.tab_cap >> 2;
+      for (uint32_t i = tid; i < n4; i += kThreads) {
+        t4[i] = make_uint4(kEmpty, kEmpty, kEmpty, kEmpty);
+        t4[n4 + i] = make_uint4(0u, 0u, 0u, 0u);
+      }
+    }
     if (tid == 0) { S.n_occ = 0; S.overflow = 0; }
     for (uint32_t i = tid; i < plan.fmap_words; i += kThreads) fbits[i] = 0u;
     const uint32_t En = (nn + kThreads - 1) / kThreads;             // contiguous neighbours per thread
