@@ -169,6 +169,7 @@ __device__ __forceinline__ void bulk_load(void* dst_smem, const void* src_gmem, 
   asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
                    smem_u32(dst_smem)), "l"(src_gmem), "r"(bytes), "r"(smem_u32(bar)) : "memory");
 }
+__device__ __forceinline__ void prefetch_l2(const void* p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
 __device__ __forceinline__ void fence_async_proxy() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 
 struct SmemLayout {
@@ -614,7 +615,7 @@ vmis_predict_kernel(const IndexView ix, const PredictArgs a, const LaunchPlan pl
       if (nd == 1) {
         // single distinct known item: S = first m postings, all similarities equal → N = first k
         nn = min(n0, K);
-        for (uint32_t i = tid; i < nn; i += kThreads) { nbr_sid[i] = P0[i]; nbr_low[i] = low0; }
+        for (uint32_t i = tid; i < nn; i += kThreads) { const uint32_t sid = P0[i]; nbr_sid[i] = sid; nbr_low[i] = low0; prefetch_l2(ix.sess_ref + sid); }
       } else {
         uint64_t* acc = acc0;
         uint64_t* out = acc1;
@@ -691,7 +692,7 @@ vmis_predict_kernel(const IndexView ix, const PredictArgs a, const LaunchPlan pl
           nn = na;
           for (uint32_t i = tid; i < na; i += kThreads) {
             const uint64_t e = acc[i];
-            nbr_sid[i] = (uint32_t)(e >> 32); nbr_low[i] = (uint32_t)e;
+            nbr_sid[i] = (uint32_t)(e >> 32); nbr_low[i] = (uint32_t)e; prefetch_l2(ix.sess_ref + (uint32_t)(e >> 32));
           }
         } else {
           // v* = max v with count(num >= v) >= K  (numerators are >= 1)
@@ -766,9 +767,9 @@ vmis_predict_kernel(const IndexView ix, const PredictArgs a, const LaunchPlan pl
             const uint64_t e = acc[i];
             const uint32_t nm = (uint32_t)e & kNumMask;
             if (nm > vstar) {
-              nbr_sid[gpos] = (uint32_t)(e >> 32); nbr_low[gpos] = (uint32_t)e; ++gpos;
+              nbr_sid[gpos] = (uint32_t)(e >> 32); nbr_low[gpos] = (uint32_t)e; ++gpos; prefetch_l2(ix.sess_ref + (uint32_t)(e >> 32));
             } else if (nm == vstar) {
-              if (pre_e < quota) { nbr_sid[tot_g + pre_e] = (uint32_t)(e >> 32); nbr_low[tot_g + pre_e] = (uint32_t)e; }
+              if (pre_e < quota) { nbr_sid[tot_g + pre_e] = (uint32_t)(e >> 32); nbr_low[tot_g + pre_e] = (uint32_t)e; prefetch_l2(ix.sess_ref + (uint32_t)(e >> 32)); }
               ++pre_e;
             }
           }
@@ -814,6 +815,7 @@ vmis_predict_kernel(const IndexView ix, const PredictArgs a, const LaunchPlan pl
     int my_len = 0;
     for (uint32_t i = i0; i < i1; ++i) {
       const uint2 r = ix.sess_ref[nbr_sid[i]];
+      prefetch_l2(ix.sess_items + (size_t)r.x * 4);                 // the inserts read this list next
       nbr_delta[i] = (uint64_t)r.x * 4; nbr_start[i] = r.y; my_len += (int)r.y;    // offset and length parked until the scan
       uint32_t low = nbr_low[i];
       if (!pos_from_lists) {                                        // reference scan (mod.rs:133-138)
