@@ -116,4 +116,42 @@ inline BatchResult predict_batch(const VMISIndex& index, const std::vector<uint6
   return r;
 }
 
+// GET /v1/recommend without the HTTP layer (recommend_resource.rs:20-65): evolving-session window over an in-process
+// store with RocksDBSessionStore semantics (sessions/mod.rs), then predict through a micro-batcher.  Thread safe.
+class Server {
+ public:
+  Server(const VMISIndex& index, size_t k, size_t m, size_t how_many, size_t max_items_in_session,
+         bool enable_business_logic = false, uint32_t max_batch = 4096, uint32_t max_wait_us = 200,
+         uint64_t session_ttl_secs = 30 * 60, uint64_t max_session_idle_secs = 20 * 60)
+      : how_many_(how_many), cap_(max_items_in_session),
+        s_(vmis_server_create(index.handle(), (uint32_t)k, (uint32_t)m, (uint32_t)how_many, (uint32_t)max_items_in_session,
+                              enable_business_logic ? 1 : 0, max_batch, max_wait_us, session_ttl_secs, max_session_idle_secs)) {
+    if (!s_) throw Error(VMIS_ERR_ARG, "vmis_server_create failed");
+  }
+  Server(const Server&) = delete;
+  Server& operator=(const Server&) = delete;
+  ~Server() { vmis_server_destroy(s_); }
+  // v1_recommend: the recommended item ids, best first
+  std::vector<uint64_t> recommend(const std::string& session_id, uint64_t item_id, bool user_consent) {
+    std::vector<uint64_t> ids(how_many_ ? how_many_ : 1);
+    const int n = vmis_server_recommend(s_, session_id.c_str(), item_id, user_consent ? 1 : 0, ids.data(), nullptr);
+    if (n < 0) throw Error(n, vmis_last_error());
+    ids.resize((size_t)n);
+    return ids;
+  }
+  // the window step alone (recommend_resource.rs:39-54)
+  std::vector<uint64_t> session_window(const std::string& session_id, uint64_t item_id, bool user_consent) {
+    std::vector<uint64_t> w(cap_ + 1);
+    const int n = vmis_server_session_window(s_, session_id.c_str(), item_id, user_consent ? 1 : 0, w.data(), w.size());
+    if (n < 0) throw Error(n, "vmis_server_session_window failed");
+    w.resize((size_t)n);
+    return w;
+  }
+  void set_clock(uint64_t epoch_secs) { vmis_server_set_clock(s_, epoch_secs); }
+
+ private:
+  size_t how_many_, cap_;
+  vmis_server_t* s_;
+};
+
 }  // namespace vmis

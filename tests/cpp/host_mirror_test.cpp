@@ -27,6 +27,24 @@ int main() {
   threw = false;
   try { vmis::VMISIndex::new_from_csv("/nonexistent/train.txt", 500, 1.0, VMIS_DEVICE_NONE); } catch (const vmis::Error& e) { threw = e.code == VMIS_ERR_IO; }
   CHECK(threw);
+  threw = false;
+  try { vmis::VMISIndex::new_("/nonexistent/index_dir", VMIS_DEVICE_NONE); } catch (const vmis::Error& e) { threw = e.code == VMIS_ERR_IO; }
+  CHECK(threw);                                                        // VMISIndex::new on a missing directory
+  {
+    // recommend_resource.rs:39-54: window of max_items_in_session items, repeats of the last item are not appended
+    vmis::Server srv(index, 5, 5, 5, 2);
+    srv.set_clock(1000000);
+    CHECK((srv.session_window("s", 7, true) == std::vector<uint64_t>{7}));
+    CHECK((srv.session_window("s", 7, true) == std::vector<uint64_t>{7}));
+    CHECK((srv.session_window("s", 8, true) == std::vector<uint64_t>{7, 8}));
+    CHECK((srv.session_window("s", 9, true) == std::vector<uint64_t>{8, 9}));
+    CHECK((srv.session_window("s", 1, false) == std::vector<uint64_t>{1}));
+    srv.set_clock(1000000 + 20 * 60 + 1);                               // idle for more than 20 minutes: starts over
+    CHECK((srv.session_window("s", 3, true) == std::vector<uint64_t>{3}));
+    threw = false;
+    try { srv.recommend("s", 920005, true); } catch (const vmis::Error& e) { threw = e.code == VMIS_ERR_CUDA; }
+    CHECK(threw);                                                      // host-only handle: no CPU fallback
+  }
   std::printf("host mirror ok\n");
   return 0;
 }
