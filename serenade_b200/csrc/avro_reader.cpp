@@ -23,6 +23,7 @@
 #include <zlib.h>
 
 #include <algorithm>
+#include <cstdint>
 #include <atomic>
 #include <cstring>
 #include <map>
@@ -265,6 +266,7 @@ struct Decoder {
       int64_t n = c.zigzag();
       if (c.err) return false;
       if (n == 0) return true;
+      if (n == INT64_MIN) return c.fail("block count out of range");
       if (n < 0) { n = -n; (void)c.zigzag(); if (c.err) return false; }
       for (int64_t i = 0; i < n; ++i) if (!item()) return false;
     }
@@ -323,6 +325,7 @@ struct Decoder {
 // ------------------------------------------------------------------------------------------------ codecs
 bool inflate_raw(const uint8_t* src, size_t n, std::vector<uint8_t>* out, std::string* err) {
   z_stream z; std::memset(&z, 0, sizeof z);
+  if (n > 0x7FFFFFFFu) { *err = "deflate block larger than 2 GiB"; return false; }
   if (inflateInit2(&z, -15) != Z_OK) { *err = "zlib init failed"; return false; }
   out->resize(std::max<size_t>(n * 4, 1 << 16));
   z.next_in = const_cast<Bytef*>(src); z.avail_in = (uInt)n;
@@ -423,6 +426,7 @@ bool read_container(const std::string& path, F&& on_record, std::string* err) {
     int64_t n = c.zigzag();
     if (c.err) return bad(c.err);
     if (n == 0) break;
+    if (n == INT64_MIN) return bad("corrupt header");
     if (n < 0) { n = -n; (void)c.zigzag(); }
     for (int64_t i = 0; i < n; ++i) {
       const int64_t kl = c.zigzag(); if (c.err || kl < 0 || !c.need((uint64_t)kl)) return bad("corrupt header");
