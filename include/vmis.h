@@ -138,6 +138,11 @@ vmis_index_t* vmis_index_from_parts(const uint64_t* item_ids, const uint64_t* po
                                     const uint64_t* sess_off, const uint32_t* sess_ts, size_t n_sessions, int device,
                                     uint32_t shard, uint32_t n_shards);
 int vmis_index_prebuilt_info(const vmis_index_t* index, vmis_prebuilt_info_t* out);
+/* The reverse direction: writes the index in that on-disk format (the reference computes it offline with Spark), so an
+ * index built on the GPU can be served by the reference: <base_path>/itemindex/part-NNNNN.avro and
+ * <base_path>/sessionindex/part-NNNNN.avro, codec "null" or "deflate" (NULL = deflate), n_files parts each.  Needs a
+ * handle that still has its host mirror of the sessions (built from a TSV, session arrays or Avro). */
+int vmis_index_to_avro(const vmis_index_t* index, const char* base_path, const char* codec, uint32_t n_files);
 
 /* ---- serialised index blob (fast restart; the reference rebuilds from CSV or re-reads Avro at start-up,
  * serving.rs:37-52).  The blob holds the flat HBM arrays of one handle (one shard).  A loaded handle has no host

@@ -23,6 +23,8 @@
 #include <zlib.h>
 
 #include <algorithm>
+#include <cerrno>
+#include <cstdio>
 #include <cstdint>
 #include <atomic>
 #include <cstring>
@@ -616,6 +618,123 @@ bool read_index_from_avro(const std::string& base_path, PrebuiltIndex* out, Avro
     ss.ts[s] = c.ts[r];
   }
   if (info) { info->item_files = item_files.size(); info->session_files = session_files.size(); info->item_records = n_rec; info->session_records = n_srec; }
+  return true;
+}
+
+// ------------------------------------------------------------------------------------------------ writer
+namespace {
+
+struct Out {
+  std::vector<uint8_t> b;
+  void zigzag(int64_t v) {
+    uint64_t u = ((uint64_t)v << 1) ^ (uint64_t)(v >> 63);
+    while (u >= 0x80) { b.push_back((uint8_t)(u | 0x80)); u >>= 7; }
+    b.push_back((uint8_t)u);
+  }
+  void bytes(const void* p, size_t n) { const uint8_t* c = static_cast<const uint8_t*>(p); b.insert(b.end(), c, c + n); }
+  void str(const std::string& s) { zigzag((int64_t)s.size()); bytes(s.data(), s.size()); }
+};
+
+const char* kItemSchema =
+    "{\"type\":\"record\",\"name\":\"ItemIndex\",\"fields\":[{\"name\":\"ItemId\",\"type\":\"long\"},"
+    "{\"name\":\"session_indices_time_ordered\",\"type\":{\"type\":\"array\",\"items\":\"int\"}},"
+    "{\"name\":\"idf\",\"type\":\"double\"},{\"name\":\"ForSale\",\"type\":\"boolean\"},"
+    "{\"name\":\"IsAdult\",\"type\":\"boolean\"}]}";
+const char* kSessionSchema =
+    "{\"type\":\"record\",\"name\":\"SessionIndex\",\"fields\":[{\"name\":\"SessionIndex\",\"type\":\"int\"},"
+    "{\"name\":\"item_ids_asc\",\"type\":{\"type\":\"array\",\"items\":\"long\"}},"
+    "{\"name\":\"Time\",\"type\":\"int\"}]}";
+
+// One container file: records [lo, hi) produced by encode(i, out), blocks of ~1 MiB of encoded records.
+template <class F>
+bool write_container_file(const std::string& path, const char* schema, bool use_deflate, size_t lo, size_t hi, uint64_t seed,
+                          F&& encode, std::string* err) {
+  FILE* f = std::fopen(path.c_str(), "wb");
+  if (!f) { *err = "cannot create " + path; return false; }
+  uint8_t sync[16];
+  for (int i = 0; i < 16; ++i) { seed = seed * 6364136223846793005ull + 1442695040888963407ull; sync[i] = (uint8_t)(seed >> 56); }
+  Out h;
+  h.bytes("Obj\x01", 4);
+  h.zigzag(2);
+  h.str("avro.schema"); h.str(schema);
+  h.str("avro.codec"); h.str(use_deflate ? "deflate" : "null");
+  h.zigzag(0);
+  h.bytes(sync, 16);
+  bool ok = std::fwrite(h.b.data(), 1, h.b.size(), f) == h.b.size();
+  Out blk; std::vector<uint8_t> comp;
+  size_t in_block = 0;
+  auto flush = [&]() {
+    if (!in_block) return;
+    const std::vector<uint8_t>* payload = &blk.b;
+    if (use_deflate) {
+      z_stream z; std::memset(&z, 0, sizeof z);
+      if (deflateInit2(&z, Z_BEST_SPEED, Z_DEFLATED, -15, 8, Z_DEFAULT_STRATEGY) != Z_OK) { ok = false; return; }
+      comp.resize(deflateBound(&z, (uLong)blk.b.size()));
+      z.next_in = blk.b.data(); z.avail_in = (uInt)blk.b.size();
+      z.next_out = comp.data(); z.avail_out = (uInt)comp.size();
+      if (deflate(&z, Z_FINISH) != Z_STREAM_END) ok = false;
+      comp.resize(z.total_out);
+      deflateEnd(&z);
+      payload = &comp;
+    }
+    Out hd; hd.zigzag((int64_t)in_block); hd.zigzag((int64_t)payload->size());
+    ok = ok && std::fwrite(hd.b.data(), 1, hd.b.size(), f) == hd.b.size() &&
+         std::fwrite(payload->data(), 1, payload->size(), f) == payload->size() && std::fwrite(sync, 1, 16, f) == 16;
+    blk.b.clear(); in_block = 0;
+  };
+  for (size_t i = lo; i < hi && ok; ++i) {
+    if (encode(i, blk)) ++in_block;
+    if (blk.b.size() >= (size_t(1) << 20)) flush();
+  }
+  flush();
+  ok = (std::fclose(f) == 0) && ok;
+  if (!ok) *err = "write to " + path + " failed";
+  return ok;
+}
+
+}  // namespace
+
+bool write_index_to_avro(const std::string& base_path, const PrebuiltIndex& p, const std::string& codec, size_t n_files,
+                         std::string* err) {
+  const bool deflate = codec == "deflate";
+  if (!deflate && codec != "null") { *err = "codec must be \"null\" or \"deflate\""; return false; }
+  if (n_files == 0) n_files = 1;
+  for (const char* sub : {"", "/itemindex", "/sessionindex"}) {
+    const std::string d = base_path + sub;
+    if (mkdir(d.c_str(), 0777) != 0 && errno != EEXIST) { *err = "cannot create directory " + d; return false; }
+  }
+  const size_t I = p.item_ids.size(), S = p.sessions.size();
+  std::vector<std::string> errs(2 * n_files);
+  std::vector<std::thread> th;
+  for (size_t fidx = 0; fidx < n_files; ++fidx) {
+    th.emplace_back([&, fidx]() {
+      char name[64]; std::snprintf(name, sizeof name, "/part-%05zu.avro", fidx);
+      write_container_file(base_path + "/itemindex" + name, kItemSchema, deflate, I * fidx / n_files, I * (fidx + 1) / n_files,
+                           0x1234 + fidx, [&](size_t i, Out& o) {
+        o.zigzag((int64_t)p.item_ids[i]);                                   // ItemId: long (`as u64` on the way back)
+        const uint64_t a = p.post_off[i], b = p.post_off[i + 1];
+        if (b > a) { o.zigzag((int64_t)(b - a)); for (uint64_t e = a; e < b; ++e) o.zigzag((int64_t)(int32_t)p.post_sessions[e]); }
+        o.zigzag(0);
+        o.bytes(&p.idf[i], 8);
+        o.b.push_back((p.attr[i] & VMIS_ATTR_FOR_SALE) ? 1 : 0);
+        o.b.push_back((p.attr[i] & VMIS_ATTR_ADULT) ? 1 : 0);
+        return true;
+      }, &errs[2 * fidx]);
+      write_container_file(base_path + "/sessionindex" + name, kSessionSchema, deflate, S * fidx / n_files,
+                           S * (fidx + 1) / n_files, 0x9876 + fidx, [&](size_t s, Out& o) {
+        const uint64_t a = p.sessions.off[s], b = p.sessions.off[s + 1];
+        if (b == a) return false;                                           // unused session index
+        o.zigzag((int64_t)s);
+        o.zigzag((int64_t)(b - a));
+        for (uint64_t e = a; e < b; ++e) o.zigzag((int64_t)p.sessions.items[e]);
+        o.zigzag(0);
+        o.zigzag((int64_t)(int32_t)p.sessions.ts[s]);
+        return true;
+      }, &errs[2 * fidx + 1]);
+    });
+  }
+  for (auto& t : th) t.join();
+  for (auto& e : errs) if (!e.empty()) { *err = e; return false; }
   return true;
 }
 

@@ -32,6 +32,13 @@ struct AvroLoadInfo {
 // :214-226 and :289-290).  Returns false and sets err on any I/O, framing, codec or schema problem.
 bool read_index_from_avro(const std::string& base_path, PrebuiltIndex* out, AvroLoadInfo* info, std::string* err);
 
+// The reverse direction: writes `p` as <base_path>/itemindex/part-NNNNN.avro and <base_path>/sessionindex/part-NNNNN.avro
+// with the record layouts of vmis_index.rs:184-192 / :249-255 (what the reference's offline Spark job produces), so an
+// index built on the GPU can be served by the reference itself.  codec: "null" or "deflate".  Sessions without items
+// are not written.
+bool write_index_to_avro(const std::string& base_path, const PrebuiltIndex& p, const std::string& codec, size_t n_files,
+                         std::string* err);
+
 // Outcome of checking / normalising a pre-computed index (build_flat_index_prebuilt).
 struct PrebuiltInfo {
   uint64_t lists_reordered = 0;    // posting lists that were not in (timestamp desc, session idx desc) order

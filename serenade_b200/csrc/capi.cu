@@ -513,6 +513,39 @@ int vmis_index_prebuilt_info(const vmis_index_t* ix, vmis_prebuilt_info_t* out) 
   return VMIS_OK;
 }
 
+// The index in the production on-disk format (the reference computes it offline with Spark; vmis_index.rs:85-313 reads
+// it back): posting lists as reference session indices, idf, attributes, and the host mirror of the sessions.
+int vmis_index_to_avro(const vmis_index_t* ix, const char* base_path, const char* codec, uint32_t n_files) {
+  if (!ix || !base_path) return fail(VMIS_ERR_ARG, "NULL argument");
+  if (ix->sessions.size() == 0) return fail(VMIS_ERR_ARG, "this handle has no host mirror of the sessions (blob-loaded or device-generated)");
+  if (ix->flat.n_shards != 1) return fail(VMIS_ERR_ARG, "export an unsharded handle");
+  const vmis::FlatIndex& F = ix->flat;
+  const size_t I = F.item_key.size();
+  std::vector<uint2> post_ref = F.post_ref;
+  std::vector<uint32_t> postings = F.postings, rank_to_orig = F.rank_to_orig;
+  if (post_ref.empty() || postings.empty() || rank_to_orig.empty()) {                // the arrays live in HBM only
+    if (ix->device == VMIS_DEVICE_NONE) return fail(VMIS_ERR_ARG, "index arrays are missing");
+    CU_TRY(cudaSetDevice(ix->device));
+    CU_TRY(cudaDeviceSynchronize());
+    post_ref.resize(I); postings.resize(ix->n_post_entries); rank_to_orig.resize(ix->view.n_kept);
+    CU_TRY(cudaMemcpy(post_ref.data(), ix->view.post_ref, I * sizeof(uint2), cudaMemcpyDeviceToHost));
+    if (!postings.empty()) CU_TRY(cudaMemcpy(postings.data(), ix->view.post_shard[0], postings.size() * 4, cudaMemcpyDeviceToHost));
+    if (!rank_to_orig.empty()) CU_TRY(cudaMemcpy(rank_to_orig.data(), ix->view.rank_to_orig, rank_to_orig.size() * 4, cudaMemcpyDeviceToHost));
+  }
+  vmis::PrebuiltIndex P;
+  P.item_ids = F.item_key; P.idf = F.idf; P.attr = F.attr;
+  P.post_off.assign(1, 0);
+  for (size_t d = 0; d < I; ++d) {
+    const uint2 ref = post_ref[d];
+    for (uint32_t i = 0; i < ref.y; ++i) P.post_sessions.push_back(rank_to_orig[postings[(size_t)ref.x * 4 + i]]);
+    P.post_off.push_back(P.post_sessions.size());
+  }
+  P.sessions = ix->sessions;
+  std::string err;
+  if (!vmis::write_index_to_avro(base_path, P, codec ? codec : "deflate", n_files ? n_files : 1, &err)) return fail(VMIS_ERR_IO, "%s", err.c_str());
+  return VMIS_OK;
+}
+
 // ---- serialised index blob: the "checkpoint" of this path (the reference rebuilds or re-reads Avro at start-up,
 // serving.rs:37-52; loading the flat arrays is a plain read + upload) ----
 int vmis_index_save(const vmis_index_t* ix, const char* path) {

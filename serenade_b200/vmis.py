@@ -63,6 +63,7 @@ def load_library():
         "vmis_index_from_avro_sharded": (vp, [C.c_char_p, i32, u32, u32]),
         "vmis_index_from_parts": (vp, [_u64p, _u64p, _u32p, _f64p, _u8p, sz, _u64p, _u64p, _u32p, sz, i32, u32, u32]),
         "vmis_index_prebuilt_info": (i32, [vp, C.POINTER(_PrebuiltInfo)]),
+        "vmis_index_to_avro": (i32, [vp, C.c_char_p, C.c_char_p, u32]),
         "vmis_index_save": (i32, [vp, C.c_char_p]),
         "vmis_index_load": (vp, [C.c_char_p, i32]),
         "vmis_index_export_shard": (i32, [vp, vp]),
@@ -110,7 +111,7 @@ EXPORTED_SYMBOLS = ("vmis_index_from_csv", "vmis_index_from_csv_ex", "vmis_index
                     "vmis_index_from_sessions_sharded", "vmis_index_export_shard", "vmis_index_attach_shard",
                     "vmis_index_attach_shard_ptr", "vmis_index_shard_ptr", "vmis_index_from_device_sessions",
                     "vmis_index_synth", "vmis_index_from_avro", "vmis_index_from_avro_sharded", "vmis_index_from_parts",
-                    "vmis_index_prebuilt_info", "vmis_index_save", "vmis_index_load",
+                    "vmis_index_prebuilt_info", "vmis_index_to_avro", "vmis_index_save", "vmis_index_load",
                     "vmis_index_set_attributes", "vmis_index_free", "vmis_index_stats", "vmis_predict_batch",
                     "vmis_predict_batch_device", "vmis_predict", "vmis_find_neighbors_batch", "vmis_items_for_session",
                     "vmis_idf", "vmis_find_attributes", "vmis_postings", "vmis_session_timestamp",
@@ -226,6 +227,10 @@ class VMISIndex:
         pi = _PrebuiltInfo()
         _check(load_library().vmis_index_prebuilt_info(self._h, C.byref(pi)))
         return {n: getattr(pi, n) for n, _ in _PrebuiltInfo._fields_}
+
+    def to_avro(self, base_path, codec="deflate", n_files=1):
+        """write the index in the production on-disk format that ``VMISIndex::new`` reads (itemindex/ + sessionindex/)"""
+        _check(load_library().vmis_index_to_avro(self._h, os.fsencode(base_path), codec.encode(), n_files))
 
     def save(self, path):
         """serialise the HBM arrays of this handle (fast restart)"""

@@ -186,3 +186,72 @@ def parts_from_oracle(oix, items, off, ts):
                 post_sessions=np.array(post, dtype=np.uint32), idf=np.array(idf, dtype=np.float64),
                 attr=np.array(attr, dtype=np.uint8), items=np.asarray(items, dtype=np.uint64),
                 off=np.asarray(off, dtype=np.uint64), ts=np.asarray(ts, dtype=np.uint32))
+
+
+# ---- independent reader for the two plain layouts (checks the C++ WRITER without going through the C++ reader) ----
+def _rd_long(b, p):
+    u, shift = 0, 0
+    while True:
+        c = b[p]
+        p += 1
+        u |= (c & 0x7F) << shift
+        shift += 7
+        if not c & 0x80:
+            break
+    return (u >> 1) ^ -(u & 1), p
+
+
+def read_container_plain(path, kind):
+    """→ list of records of an `item` / `session` container written with the plain schema (null or deflate codec)"""
+    b = open(path, "rb").read()
+    assert b[:4] == b"Obj\x01"
+    p, meta = 4, {}
+    while True:
+        n, p = _rd_long(b, p)
+        if n == 0:
+            break
+        for _ in range(abs(n)):
+            kl, p = _rd_long(b, p); k = b[p:p + kl]; p += kl
+            vl, p = _rd_long(b, p); meta[k.decode()] = b[p:p + vl]; p += vl
+    sync = b[p:p + 16]
+    p += 16
+    schema = json.loads(meta["avro.schema"])
+    codec = meta.get("avro.codec", b"null").decode()
+    out = []
+    while p < len(b):
+        count, p = _rd_long(b, p)
+        size, p = _rd_long(b, p)
+        raw = b[p:p + size]
+        p += size
+        assert b[p:p + 16] == sync
+        p += 16
+        if codec == "deflate":
+            raw = zlib.decompress(raw, -15)
+        q = 0
+        for _ in range(count):
+            def arr(q):
+                vals = []
+                while True:
+                    n, q = _rd_long(raw, q)
+                    if n == 0:
+                        return vals, q
+                    if n < 0:
+                        n = -n
+                        _, q = _rd_long(raw, q)
+                    for _ in range(n):
+                        v, q = _rd_long(raw, q)
+                        vals.append(v)
+            if kind == "item":
+                item, q = _rd_long(raw, q)
+                sess, q = arr(q)
+                idf = struct.unpack("<d", raw[q:q + 8])[0]
+                q += 8
+                out.append((item & ((1 << 64) - 1), [s & 0xFFFFFFFF for s in sess], idf, bool(raw[q]), bool(raw[q + 1])))
+                q += 2
+            else:
+                idx, q = _rd_long(raw, q)
+                items, q = arr(q)
+                t, q = _rd_long(raw, q)
+                out.append((idx, [i & ((1 << 64) - 1) for i in items], t & 0xFFFFFFFF))
+        assert q == len(raw)
+    return schema, out

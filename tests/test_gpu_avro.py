@@ -125,3 +125,17 @@ def test_avro_index_item_sharded(sb, oracle, tmp_path):
     qs = _queries(rng, np.unique(items), 200)
     for sh in shards:
         _equal(sb, sh, oix, qs, 20, 25, 21)
+
+
+def test_device_built_index_exports_and_reloads(sb, oracle, tmp_path):
+    """index built on the device → vmis_index_to_avro → VMISIndex::new: the reloaded index answers identically"""
+    items, off, ts = sb.synth_sessions(42, 3000, 30000)
+    gix = sb.VMISIndex.from_sessions(items, off, ts, 300, 34, 2.0, device=0)
+    gix.to_avro(str(tmp_path), "deflate", 4)
+    back = sb.VMISIndex.new(str(tmp_path), device=0)
+    assert back.prebuilt_info()["m_carry"] == 300 and back.prebuilt_info()["lists_reordered"] == 0
+    q = sb.synth_queries(43, 3000, 2000, 4)
+    a = sb.predict_batch(gix, q, 100, 300, 21)
+    b = sb.predict_batch(back, q, 100, 300, 21)
+    for x, y in zip(a, b):
+        assert np.array_equal(x, y)
