@@ -6,11 +6,14 @@
 #include "avro_reader.h"
 
 #include <algorithm>
+#include <atomic>
 #include <cmath>
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <mutex>
 #include <numeric>
+#include <thread>
 
 namespace vmis {
 namespace {
@@ -337,63 +340,89 @@ bool build_flat_index_prebuilt(const PrebuiltIndex& p, uint32_t n_shards, FlatIn
   std::vector<uint32_t> rank_of(S, kEmpty);
   for (size_t r = 0; r < Sk; ++r) { F.rank_to_orig[r] = (uint32_t)(order[r] & 0xFFFFFFFFull); rank_of[F.rank_to_orig[r]] = (uint32_t)r; }
 
+  // Steps 3-5 run over ranges of sessions / items on all host cores; the first problem found wins.
+  std::mutex err_mu; std::string first_err;
+  auto report = [&](const std::string& m) { std::lock_guard<std::mutex> g(err_mu); if (first_err.empty()) first_err = m; };
+  auto parallel_for = [&](size_t n, auto&& body) {
+    const size_t nt = std::max<size_t>(1, std::min<size_t>(std::thread::hardware_concurrency(), (n + 4095) / 4096));
+    std::vector<std::thread> th;
+    for (size_t t = 1; t < nt; ++t) th.emplace_back([&, t]() { body(n * t / nt, n * (t + 1) / nt); });
+    body(0, n / nt);
+    for (auto& x : th) x.join();
+  };
+
   // 3. session -> items (dense, ascending), 16-byte aligned starts
   F.sess_ref.resize(Sk);
   uint64_t P = 0; uint32_t max_len = 0;
-  std::vector<uint32_t> tmp;
-  for (size_t r = 0; r < Sk; ++r) {
-    const uint32_t o = F.rank_to_orig[r];
-    const uint32_t len = (uint32_t)(s.off[o + 1] - s.off[o]);
-    tmp.resize(len);
-    for (uint32_t t = 0; t < len; ++t) {
-      tmp[t] = host_lookup_item(F, s.items[s.off[o] + t]);
-      if (tmp[t] == kEmpty) {
-        *err = "session " + std::to_string(o) + " holds item " + std::to_string(s.items[s.off[o] + t]) +
-               ", which has no itemindex record (the reference panics at vmis_index.rs:322)";
-        return false;
-      }
+  {
+    uint64_t start = 0;
+    for (size_t r = 0; r < Sk; ++r) {
+      const uint32_t o = F.rank_to_orig[r];
+      const uint32_t len = (uint32_t)(s.off[o + 1] - s.off[o]);
+      if ((start >> 2) > 0xFFFFFFFFull) { *err = "session item array too large"; return false; }
+      F.sess_ref[r] = make_uint2((uint32_t)(start >> 2), len);
+      start += (len + 3u) & ~3u;
+      P += len; max_len = std::max(max_len, len);
     }
-    std::sort(tmp.begin(), tmp.end());
-    for (uint32_t t = 1; t < len; ++t) if (tmp[t] == tmp[t - 1]) { *err = "duplicate item inside session " + std::to_string(o); return false; }
-    const size_t start = F.sess_items.size();
-    if ((start >> 2) > 0xFFFFFFFFull) { *err = "session item array too large"; return false; }
-    F.sess_ref[r] = make_uint2((uint32_t)(start >> 2), len);
-    F.sess_items.insert(F.sess_items.end(), tmp.begin(), tmp.end());
-    while (F.sess_items.size() & 3) F.sess_items.push_back(kEmpty);
-    P += len; max_len = std::max(max_len, len);
+    F.sess_items.assign(start, kEmpty);
   }
+  parallel_for(Sk, [&](size_t r0, size_t r1) {
+    for (size_t r = r0; r < r1; ++r) {
+      const uint32_t o = F.rank_to_orig[r];
+      const uint2 ref = F.sess_ref[r];
+      uint32_t* dst = &F.sess_items[(size_t)ref.x * 4];
+      for (uint32_t t = 0; t < ref.y; ++t) {
+        dst[t] = host_lookup_item(F, s.items[s.off[o] + t]);
+        if (dst[t] == kEmpty) {
+          report("session " + std::to_string(o) + " holds item " + std::to_string(s.items[s.off[o] + t]) +
+                 ", which has no itemindex record (the reference panics at vmis_index.rs:322)");
+          return;
+        }
+      }
+      std::sort(dst, dst + ref.y);
+      for (uint32_t t = 1; t < ref.y; ++t) if (dst[t] == dst[t - 1]) { report("duplicate item inside session " + std::to_string(o)); return; }
+    }
+  });
+  if (!first_err.empty()) { *err = first_err; return false; }
   F.n_pairs_kept = P; F.max_len = max_len;
 
   // 4. postings as time ranks, descending; lists in another order (or with repeats) are normalised
   F.post_ref.resize(I);
-  std::vector<uint64_t> shard_size(n_shards, 0);
   std::vector<std::vector<uint32_t>> lists(I);
+  std::atomic<uint64_t> n_reordered{0}, n_dups{0};
+  parallel_for(I, [&](size_t d0, size_t d1) {
+    for (size_t d = d0; d < d1; ++d) {
+      const uint32_t src = by_key[d];
+      std::vector<uint32_t>& L = lists[d];
+      L.reserve(p.post_off[src + 1] - p.post_off[src]);
+      bool sorted = true;
+      for (uint64_t e = p.post_off[src]; e < p.post_off[src + 1]; ++e) {
+        const uint32_t r = rank_of[p.post_sessions[e]];
+        const uint2 ref = F.sess_ref[r];
+        const uint32_t* it = &F.sess_items[(size_t)ref.x * 4];
+        if (!std::binary_search(it, it + ref.y, (uint32_t)d)) {
+          report("the posting list of item " + std::to_string(F.item_key[d]) + " names session " +
+                 std::to_string(p.post_sessions[e]) + ", which does not contain the item");
+          return;
+        }
+        if (!L.empty() && r >= L.back()) sorted = false;
+        L.push_back(r);
+      }
+      if (!sorted) {
+        ++n_reordered;
+        std::sort(L.begin(), L.end(), [](uint32_t a, uint32_t b) { return a > b; });
+        const size_t before = L.size();
+        L.erase(std::unique(L.begin(), L.end()), L.end());
+        n_dups += before - L.size();
+      }
+    }
+  });
+  if (!first_err.empty()) { *err = first_err; return false; }
+  pi.lists_reordered = n_reordered; pi.duplicate_postings = n_dups;
+  std::vector<uint64_t> shard_size(n_shards, 0);
   uint32_t m_build = 0;
   for (size_t d = 0; d < I; ++d) {
-    const uint32_t src = by_key[d];
-    std::vector<uint32_t>& L = lists[d];
-    L.reserve(p.post_off[src + 1] - p.post_off[src]);
-    bool sorted = true;
-    for (uint64_t e = p.post_off[src]; e < p.post_off[src + 1]; ++e) {
-      const uint32_t r = rank_of[p.post_sessions[e]];
-      const uint2 ref = F.sess_ref[r];
-      const uint32_t* it = &F.sess_items[(size_t)ref.x * 4];
-      if (!std::binary_search(it, it + ref.y, (uint32_t)d)) {
-        *err = "the posting list of item " + std::to_string(F.item_key[d]) + " names session " + std::to_string(p.post_sessions[e]) +
-               ", which does not contain the item";
-        return false;
-      }
-      if (!L.empty() && r >= L.back()) sorted = false;
-      L.push_back(r);
-    }
-    if (!sorted) {
-      ++pi.lists_reordered;
-      std::sort(L.begin(), L.end(), [](uint32_t a, uint32_t b) { return a > b; });
-      const size_t before = L.size();
-      L.erase(std::unique(L.begin(), L.end()), L.end());
-      pi.duplicate_postings += before - L.size();
-    }
-    const uint32_t len = (uint32_t)L.size();
+    const uint32_t len = (uint32_t)lists[d].size();
     m_build = std::max(m_build, len);
     uint64_t& sz = shard_size[d % n_shards];
     if ((sz >> 2) > 0xFFFFFFFFull) { *err = "posting array too large"; return false; }
@@ -405,28 +434,33 @@ bool build_flat_index_prebuilt(const PrebuiltIndex& p, uint32_t n_shards, FlatIn
   F.shard_begin.assign(n_shards + 1, 0);
   for (uint32_t sh = 0; sh < n_shards; ++sh) F.shard_begin[sh + 1] = F.shard_begin[sh] + shard_size[sh];
   F.postings.assign(F.shard_begin[n_shards], kEmpty);
-  for (size_t d = 0; d < I; ++d)
-    std::copy(lists[d].begin(), lists[d].end(), F.postings.begin() + F.shard_begin[d % n_shards] + (size_t)F.post_ref[d].x * 4);
+  parallel_for(I, [&](size_t d0, size_t d1) {
+    for (size_t d = d0; d < d1; ++d)
+      std::copy(lists[d].begin(), lists[d].end(), F.postings.begin() + F.shard_begin[d % n_shards] + (size_t)F.post_ref[d].x * 4);
+  });
 
   // 5. m_carry: the kernel may take the first-match position of mod.rs:133-138 from the merged lists only if a
   //    session of the m-sample is on the list of every evolving item it contains.  That holds for m <= the
   //    shortest list that (a) misses some session containing its item and (b) is the most-recent prefix of them.
   uint32_t m_carry = 0xFFFFFFFFu;
   {
-    std::vector<uint32_t> newer_or_listed(I, 0), df(I, 0);
-    for (size_t r = 0; r < Sk; ++r) {
-      const uint2 ref = F.sess_ref[r];
-      const uint32_t* it = &F.sess_items[(size_t)ref.x * 4];
-      for (uint32_t t = 0; t < ref.y; ++t) {
-        const uint32_t d = it[t];
-        ++df[d];
-        if (!lists[d].empty() && (uint32_t)r >= lists[d].back()) ++newer_or_listed[d];
+    std::vector<std::atomic<uint32_t>> newer_or_listed(I), df(I);
+    for (size_t d = 0; d < I; ++d) { newer_or_listed[d].store(0, std::memory_order_relaxed); df[d].store(0, std::memory_order_relaxed); }
+    parallel_for(Sk, [&](size_t r0, size_t r1) {
+      for (size_t r = r0; r < r1; ++r) {
+        const uint2 ref = F.sess_ref[r];
+        const uint32_t* it = &F.sess_items[(size_t)ref.x * 4];
+        for (uint32_t t = 0; t < ref.y; ++t) {
+          const uint32_t d = it[t];
+          df[d].fetch_add(1, std::memory_order_relaxed);
+          if (!lists[d].empty() && (uint32_t)r >= lists[d].back()) newer_or_listed[d].fetch_add(1, std::memory_order_relaxed);
+        }
       }
-    }
+    });
     for (size_t d = 0; d < I; ++d) {
       const uint32_t len = (uint32_t)lists[d].size();
-      if (len == df[d]) continue;                                  // complete list
-      if (newer_or_listed[d] != len) { m_carry = 0; break; }       // not a most-recent prefix
+      if (len == df[d].load(std::memory_order_relaxed)) continue;      // complete list
+      if (newer_or_listed[d].load(std::memory_order_relaxed) != len) { m_carry = 0; break; }   // not a most-recent prefix
       m_carry = std::min(m_carry, len);
     }
   }
