@@ -113,6 +113,17 @@ def cpu_reference(oracle_index, queries, threads, budget_s, batch_hint=4096):
     return n2 / r[3], n2, r[3]
 
 
+def cpu_single_thread_latency(oracle_index, queries, n=2000):
+    """evaluator.rs:57-89: per-call wall time of `predict` on ONE thread, percentiles in microseconds (the reference's
+    README.md:16 quotes p90 < 1.7 ms for this index size on its own hardware)."""
+    q_items, q_off = queries
+    n = min(n, len(q_off) - 1)
+    r = oracle_index.predict_batch(q_items[:q_off[n]], q_off[:n + 1], K, M, HOW_MANY, False, mode=0, threads=1,
+                                   want_latency=True, want_outputs=False)
+    lat = np.sort(r[4][n // 10:])                      # the first tenth warms the caches
+    return {f"p{str(p).replace('.', '_')}": round(float(np.percentile(lat, p)), 1) for p in (25, 50, 75, 90, 95, 99.5)}
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -174,7 +185,8 @@ def main():
                           "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u32/i32+f64",
                           "data": "synthetic", "config": cfg,
                           "cpu_baseline": {"value": v, "unit": "queries/s", "cores": threads, "kind": "port",
-                                           "sample": sample},
+                                           "sample": sample,
+                                           "single_thread_latency_us": cpu_single_thread_latency(oix, q)},
                           "e2e": {"value": v, "unit": "queries/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}))
         return 0
 
@@ -347,7 +359,8 @@ def main():
         log(f"[cpu] oracle index {time.time() - t2 - secs:.1f}s; {n_sample} queries in {secs:.1f}s on {threads} threads")
         out["cpu_baseline"] = {"value": qps, "unit": "queries/s", "cores": threads, "kind": "port",
                                "sample": f"first {n_sample} queries of the first timed batch, faithful mode, "
-                                         f"{threads} threads sharing one index"}
+                                         f"{threads} threads sharing one index",
+                               "single_thread_latency_us": cpu_single_thread_latency(oix, batches[args.warmup])}
         # spot parity inside the bench: the same sample through the canonical oracle vs the device result
         m_chk = min(2048, n_sample)
         qi, qo = batches[args.warmup]
