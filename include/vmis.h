@@ -88,6 +88,17 @@ vmis_index_t* vmis_index_from_csv(const char* path, size_t m, double idf_weighti
 /* Same, with max_training_session_length given explicitly (0 = compute p99.5). */
 vmis_index_t* vmis_index_from_csv_ex(const char* path, size_t m, double idf_weighting, size_t max_len, int device);
 
+/* read_from_file (vmis_index.rs:591-752) on its own: the training sessions of a TSV exactly as new_from_csv sees them
+ * (session index = rank of the session id, items ascending, max timestamp; incl. the last-row quirk).  For callers that
+ * build many indexes from one file — the HPO objective rebuilds the index for every trial (objective.rs:17): parse
+ * once, then vmis_index_from_sessions(..., m, max_len = 0, idf_weighting, ...) per trial gives the same index as
+ * vmis_index_from_csv.  The pointers of the view stay valid until vmis_sessions_free. */
+typedef struct vmis_sessions vmis_sessions_t;
+vmis_sessions_t* vmis_sessions_from_csv(const char* path);
+int vmis_sessions_view(const vmis_sessions_t* sessions, const uint64_t** items, const uint64_t** sess_off,
+                       const uint32_t** sess_ts, size_t* n_sessions);
+void vmis_sessions_free(vmis_sessions_t* sessions);
+
 /* prepare_hashmap(historical_sessions, timestamps, m, max_len, idf_weighting) — vmis_index.rs:422-528,
  * followed by the VMISIndex{..} assembly of :75-82.  items[sess_off[s]..sess_off[s+1]) are the item ids
  * of training session s (any order; duplicates not allowed), sess_ts[s] its max timestamp. */

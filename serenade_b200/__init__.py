@@ -4,8 +4,8 @@ The compute lives in ``libvmis_b200.so`` (hand-written sm_100a CUDA behind the C
 ``include/vmis.h``).  This package is the thin Python mirror of the reference's
 ``VMISIndex`` / ``predict`` surface used by the tests and the benchmark.
 """
-from .vmis import (Batcher, Server, md5, VMISIndex, VmisError, load_library, predict, predict_batch, synth_queries,  # noqa: F401
+from .vmis import (Batcher, Server, md5, VMISIndex, VmisError, load_library, predict, predict_batch, read_sessions_csv, synth_queries,  # noqa: F401
                    synth_sessions, DEVICE_NONE)
 
-__all__ = ["Batcher", "Server", "md5", "VMISIndex", "VmisError", "load_library", "predict", "predict_batch", "synth_sessions", "synth_queries",
+__all__ = ["Batcher", "Server", "md5", "VMISIndex", "VmisError", "load_library", "predict", "predict_batch", "read_sessions_csv", "synth_sessions", "synth_queries",
            "DEVICE_NONE"]

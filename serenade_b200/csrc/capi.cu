@@ -644,6 +644,27 @@ const void* vmis_index_shard_ptr(const vmis_index_t* ix) {
   return ix->view.post_shard[ix->shard];
 }
 
+// read_from_file (vmis_index.rs:591-752) on its own: the parsed training sessions, so that callers which build many
+// indexes from one file (the HPO objective rebuilds it for every trial, objective.rs:17) parse it once.
+struct vmis_sessions { vmis::Sessions s; };
+
+vmis_sessions_t* vmis_sessions_from_csv(const char* path) {
+  if (!path) { fail(VMIS_ERR_ARG, "path is NULL"); return nullptr; }
+  std::unique_ptr<vmis_sessions> h(new vmis_sessions());
+  std::string err;
+  if (!vmis::read_sessions_from_csv(path, &h->s, &err)) { fail(VMIS_ERR_IO, "%s", err.c_str()); return nullptr; }
+  return h.release();
+}
+
+int vmis_sessions_view(const vmis_sessions_t* h, const uint64_t** items, const uint64_t** sess_off, const uint32_t** sess_ts,
+                       size_t* n_sessions) {
+  if (!h || !items || !sess_off || !sess_ts || !n_sessions) return fail(VMIS_ERR_ARG, "NULL argument");
+  *items = h->s.items.data(); *sess_off = h->s.off.data(); *sess_ts = h->s.ts.data(); *n_sessions = h->s.size();
+  return VMIS_OK;
+}
+
+void vmis_sessions_free(vmis_sessions_t* h) { delete h; }
+
 vmis_index_t* vmis_index_from_csv_ex(const char* path, size_t m, double idf_weighting, size_t max_len, int device) {
   if (!path) { fail(VMIS_ERR_ARG, "path is NULL"); return nullptr; }
   std::unique_ptr<vmis_index> ix(new vmis_index());

@@ -12,14 +12,20 @@ import itertools
 import random
 
 from .evaluate import evaluate, read_test_sessions
-from .vmis import VMISIndex
+from .vmis import VMISIndex, read_sessions_csv
 
 
 def objective(path_to_training, test_data_file, n_most_recent_sessions, neighborhood_size_k, last_items_in_session,
-              idf_weighting, enable_business_logic=False, device=0, max_len=0, test_sessions=None):
-    """objective.rs:8-52 → Mrr@20 (qty_max_reco_results = 20, :21)."""
-    index = VMISIndex.new_from_csv(path_to_training, int(n_most_recent_sessions), float(idf_weighting), max_len=max_len,
-                                   device=device)                                     # :17, rebuilt per trial
+              idf_weighting, enable_business_logic=False, device=0, max_len=0, test_sessions=None,
+              training_sessions=None):
+    """objective.rs:8-52 → Mrr@20 (qty_max_reco_results = 20, :21).  `training_sessions` (from `read_sessions_csv`)
+    skips re-parsing the training file: the index is still REBUILT for every trial, as in the reference (:17)."""
+    if training_sessions is not None:
+        index = VMISIndex.from_sessions(*training_sessions, int(n_most_recent_sessions), max_len, float(idf_weighting),
+                                        device=device)
+    else:
+        index = VMISIndex.new_from_csv(path_to_training, int(n_most_recent_sessions), float(idf_weighting),
+                                       max_len=max_len, device=device)
     try:
         sessions = test_sessions if test_sessions is not None else read_test_sessions(test_data_file)   # :19
         res = evaluate(index, sessions, int(neighborhood_size_k), int(n_most_recent_sessions), how_many=20,
@@ -54,10 +60,12 @@ class HyperParamGrid:
 
 def _search(train_data_path, test_data_path, combos, enable_business_logic, device, max_len):
     sessions = read_test_sessions(test_data_path)
+    training = read_sessions_csv(train_data_path)                  # parsed once; every trial rebuilds the index from it
     best, best_value, records = None, float("-inf"), []
     for iteration, c in enumerate(combos):
         v = objective(train_data_path, test_data_path, c["n_most_recent_sessions"], c["neighborhood_size_k"],
-                      c["last_items_in_session"], c["idf_weighting"], enable_business_logic, device, max_len, sessions)
+                      c["last_items_in_session"], c["idf_weighting"], enable_business_logic, device, max_len, sessions,
+                      training)
         records.append((iteration, c["n_most_recent_sessions"], c["neighborhood_size_k"], c["last_items_in_session"],
                         c["idf_weighting"], v))
         if v > best_value:                                                            # exhaustive_grid_search.rs:84-90

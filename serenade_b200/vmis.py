@@ -55,6 +55,9 @@ def load_library():
     sig = {
         "vmis_index_from_csv": (vp, [C.c_char_p, sz, f64, i32]),
         "vmis_index_from_csv_ex": (vp, [C.c_char_p, sz, f64, sz, i32]),
+        "vmis_sessions_from_csv": (vp, [C.c_char_p]),
+        "vmis_sessions_view": (i32, [vp, C.POINTER(_u64p), C.POINTER(_u64p), C.POINTER(_u32p), C.POINTER(sz)]),
+        "vmis_sessions_free": (None, [vp]),
         "vmis_index_from_sessions": (vp, [_u64p, _u64p, _u32p, sz, sz, sz, f64, i32]),
         "vmis_index_from_sessions_sharded": (vp, [_u64p, _u64p, _u32p, sz, sz, sz, f64, i32, u32, u32]),
         "vmis_index_from_device_sessions": (vp, [vp, vp, vp, sz, sz, sz, f64, i32, u32, u32]),
@@ -107,7 +110,8 @@ def load_library():
     return L
 
 
-EXPORTED_SYMBOLS = ("vmis_index_from_csv", "vmis_index_from_csv_ex", "vmis_index_from_sessions",
+EXPORTED_SYMBOLS = ("vmis_index_from_csv", "vmis_index_from_csv_ex", "vmis_sessions_from_csv", "vmis_sessions_view",
+                    "vmis_sessions_free", "vmis_index_from_sessions",
                     "vmis_index_from_sessions_sharded", "vmis_index_export_shard", "vmis_index_attach_shard",
                     "vmis_index_attach_shard_ptr", "vmis_index_shard_ptr", "vmis_index_from_device_sessions",
                     "vmis_index_synth", "vmis_index_from_avro", "vmis_index_from_avro_sharded", "vmis_index_from_parts",
@@ -359,6 +363,25 @@ def predict(index, evolving_session, k, m, how_many, enable_business_logic=False
     n = _check(load_library().vmis_predict(index.handle, _p(ev, C.c_uint64), len(ev), k, m, how_many,
                                            int(enable_business_logic), _p(ids, C.c_uint64), _p(sc, C.c_double)))
     return [(int(ids[i]), float(sc[i])) for i in range(n)]
+
+
+def read_sessions_csv(path):
+    """``read_from_file`` (vmis_index.rs:591-752) → (items u64, sess_off u64, sess_ts u32), parsed once for many index
+    builds (``VMISIndex.from_sessions(items, off, ts, m, 0, idf_weighting)`` == ``VMISIndex.new_from_csv``)."""
+    L = load_library()
+    h = L.vmis_sessions_from_csv(os.fsencode(path))
+    if not h:
+        raise VmisError(L.vmis_last_error_code(), L.vmis_last_error().decode(errors="replace"))
+    h = C.c_void_p(h)
+    try:
+        pi, po, pt, n = _u64p(), _u64p(), _u32p(), C.c_size_t()
+        _check(L.vmis_sessions_view(h, C.byref(pi), C.byref(po), C.byref(pt), C.byref(n)))
+        off = np.ctypeslib.as_array(po, shape=(n.value + 1,)).copy()
+        ts = np.ctypeslib.as_array(pt, shape=(n.value,)).copy() if n.value else np.zeros(0, np.uint32)
+        items = np.ctypeslib.as_array(pi, shape=(int(off[-1]),)).copy() if off[-1] else np.zeros(0, np.uint64)
+        return items, off, ts
+    finally:
+        L.vmis_sessions_free(h)
 
 
 def synth_sessions(seed, n_items, n_sessions):

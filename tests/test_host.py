@@ -193,3 +193,18 @@ def test_cpp_host_mirror(tmp_path):
                            "-Wl,-rpath," + os.path.join(ROOT, "serenade_b200")])
     out = subprocess.run([str(exe)], capture_output=True, text=True)
     assert out.returncode == 0 and "host mirror ok" in out.stdout, out.stdout + out.stderr
+
+
+def test_sessions_parsed_once_give_the_same_index(sb, toy_dir):
+    """vmis_sessions_from_csv + from_sessions(max_len=0) == new_from_csv (the HPO loop parses the training file once)"""
+    train = os.path.join(toy_dir, "train.txt")
+    items, off, ts = sb.read_sessions_csv(train)
+    a = sb.VMISIndex.new_from_csv(train, 500, 2.0, device=sb.DEVICE_NONE)
+    b = sb.VMISIndex.from_sessions(items, off, ts, 500, 0, 2.0, device=sb.DEVICE_NONE)
+    assert a.stats() == b.stats() and a.stats()["n_sessions"] == len(ts) == 23753
+    for item in (13598, 2835, 10, 12068):
+        np.testing.assert_array_equal(a.postings(item), b.postings(item))
+        assert a.idf(item) == b.idf(item)
+    np.testing.assert_array_equal(a.items_for_session(5189), items[off[5189]:off[5189 + 1]])
+    with pytest.raises(sb.VmisError):
+        sb.read_sessions_csv("/nonexistent/train.txt")
