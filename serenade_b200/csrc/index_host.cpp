@@ -110,28 +110,92 @@ size_t session_length_p99_5(const Sessions& s) {
 bool read_sessions_from_csv(const std::string& path, Sessions* out, std::string* err) {
   FILE* f = std::fopen(path.c_str(), "rb");
   if (!f) { *err = "cannot open " + path; return false; }
-  struct Row { uint64_t session, item, time; };
-  std::vector<Row> rows;
-  char line[8192];
-  bool first = true;
-  size_t bad = 0;
-  while (std::fgets(line, sizeof line, f)) {
-    if (first) { first = false; continue; }                         // header row (:597)
-    char* e = nullptr; const char* p = line;
-    if (*p == '\n' || *p == '\r' || *p == 0) continue;
-    const unsigned long long sid = std::strtoull(p, &e, 10);
-    if (e == p || *e != '\t') { ++bad; continue; }
-    p = e + 1; const unsigned long long iid = std::strtoull(p, &e, 10);
-    if (e == p || *e != '\t') { ++bad; continue; }
-    p = e + 1; const double t = std::strtod(p, &e);
-    if (e == p) { ++bad; continue; }
-    rows.push_back(Row{sid, iid, (uint64_t)std::llround(t)});        // (usize, usize, f64.round()) :607-609
+  // The whole file in memory, every line turned into a C string; the lines are parsed on all host cores
+  // (chunks in file order, so the order of the rows is the file's) with the same strtoull / strtod calls a
+  // line-by-line reader would make.
+  std::vector<char> buf;
+  {
+    std::fseek(f, 0, SEEK_END);
+    const long sz = std::ftell(f);
+    std::fseek(f, 0, SEEK_SET);
+    if (sz < 0) { std::fclose(f); *err = "cannot read " + path; return false; }
+    buf.resize((size_t)sz + 1);
+    const size_t got = std::fread(buf.data(), 1, (size_t)sz, f);
+    std::fclose(f);
+    buf.resize(got + 1);
+    buf[got] = 0;
   }
-  std::fclose(f);
+  const size_t size = buf.size() - 1;
+  struct Row { uint64_t session, item, time; };
+  const size_t nt = std::max<size_t>(1, std::min<size_t>(std::thread::hardware_concurrency(), size / (1 << 20) + 1));
+  std::vector<std::vector<Row>> parts(nt);
+  std::vector<size_t> bad_rows(nt, 0);
+  {
+    std::vector<std::thread> th;
+    auto terminate_lines = [&](size_t t) {
+      for (size_t i = size * t / nt, e = size * (t + 1) / nt; i < e; ++i) if (buf[i] == '\n') buf[i] = 0;
+    };
+    for (size_t t = 1; t < nt; ++t) th.emplace_back(terminate_lines, t);
+    terminate_lines(0);
+    for (auto& x : th) x.join();
+    th.clear();
+    auto parse = [&](size_t t) {
+      size_t pos = size * t / nt;
+      const size_t end = size * (t + 1) / nt;
+      if (t == 0) { while (pos < size && buf[pos] != 0) ++pos; ++pos; }           // header row (:597)
+      else if (pos > 0 && buf[pos - 1] != 0) { while (pos < size && buf[pos] != 0) ++pos; ++pos; }   // inside a line: it belongs to the previous chunk
+      std::vector<Row>& rows = parts[t];
+      rows.reserve((end - std::min(pos, end)) / 24 + 16);
+      while (pos < end) {                                                          // lines STARTING in [begin, end)
+        const char* p = buf.data() + pos;
+        const size_t len = std::strlen(p);
+        pos += len + 1;
+        if (len == 0 || *p == '\r') continue;
+        char* e = nullptr;
+        const unsigned long long sid = std::strtoull(p, &e, 10);
+        if (e == p || *e != '\t') { ++bad_rows[t]; continue; }
+        p = e + 1; const unsigned long long iid = std::strtoull(p, &e, 10);
+        if (e == p || *e != '\t') { ++bad_rows[t]; continue; }
+        p = e + 1; const double tm = std::strtod(p, &e);
+        if (e == p) { ++bad_rows[t]; continue; }
+        rows.push_back(Row{sid, iid, (uint64_t)std::llround(tm)});                 // (usize, usize, f64.round()) :607-609
+      }
+    };
+    for (size_t t = 1; t < nt; ++t) th.emplace_back(parse, t);
+    parse(0);
+    for (auto& x : th) x.join();
+  }
+  size_t bad = 0, total = 0;
+  for (size_t t = 0; t < nt; ++t) { bad += bad_rows[t]; total += parts[t].size(); }
   if (bad) std::fprintf(stderr, "vmis: %zu unparsable rows skipped in %s\n", bad, path.c_str());
+  std::vector<Row> rows(total);
+  std::vector<size_t> begin(nt + 1, 0);
+  for (size_t t = 0; t < nt; ++t) begin[t + 1] = begin[t] + parts[t].size();
+  {
+    // rows grouped by session id, file order kept inside a session (stable, :620-633): every chunk is copied into
+    // place and stable-sorted on its own thread, then neighbouring runs are merged (std::inplace_merge is stable)
+    std::vector<std::thread> th;
+    auto by_session = [](const Row& a, const Row& b) { return a.session < b.session; };
+    auto sort_part = [&](size_t t) {
+      std::copy(parts[t].begin(), parts[t].end(), rows.begin() + begin[t]);
+      std::vector<Row>().swap(parts[t]);
+      std::stable_sort(rows.begin() + begin[t], rows.begin() + begin[t + 1], by_session);
+    };
+    for (size_t t = 1; t < nt; ++t) th.emplace_back(sort_part, t);
+    sort_part(0);
+    for (auto& x : th) x.join();
+    for (size_t width = 1; width < nt; width *= 2) {
+      th.clear();
+      for (size_t lo = 0; lo + width < nt; lo += 2 * width) {
+        const size_t mid = lo + width, hi = std::min(nt, lo + 2 * width);
+        th.emplace_back([&, lo, mid, hi]() {
+          std::inplace_merge(rows.begin() + begin[lo], rows.begin() + begin[mid], rows.begin() + begin[hi], by_session);
+        });
+      }
+      for (auto& x : th) x.join();
+    }
+  }
   if (rows.empty()) { *err = "no rows in " + path; return false; }
-  // rows grouped by session id, file order kept inside a session (stable, :620-633)
-  std::stable_sort(rows.begin(), rows.end(), [](const Row& a, const Row& b) { return a.session < b.session; });
   const size_t n = rows.size();
   out->items.clear(); out->off.assign(1, 0); out->ts.clear();
   std::vector<uint64_t> cur; cur.push_back(rows[0].item);
