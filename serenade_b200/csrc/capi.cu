@@ -77,6 +77,9 @@ struct vmis_index {
 
 namespace {
 
+// IndexView::g32 from the uploaded idf array (one small kernel); owned by the handle like the other arrays
+int attach_g32(vmis_index* ix);
+
 template <class T>
 int upload(vmis_index* ix, const std::vector<T>& v, const T** out) {
   void* d = nullptr;
@@ -173,6 +176,7 @@ vmis_index* upload_flat(std::unique_ptr<vmis_index> ix, int device, uint32_t sha
   V.m_build = F.m_build;
   V.m_carry = F.m_carry;
   V.max_len = F.max_len;
+  if (attach_g32(ix.get())) { for (void* d : ix->dev_allocs) cudaFree(d); return nullptr; }
   ix->n_post_entries = own.size();
   ix->n_sess_item_entries = F.sess_items.size();
   // the big CSR arrays now live in HBM only
@@ -203,7 +207,20 @@ vmis_index* adopt_device_index(std::unique_ptr<vmis_index> ix, vmis::DeviceIndex
   ix->n_sess_item_entries = A.sess_items_entries;
   ix->device_bytes = A.n_items * 8 + A.item_hash_cap * sizeof(vmis::ItemHashEntry) + A.n_items * 8 + A.shard_entries * 4 +
                      A.n_kept * 8 + A.sess_items_entries * 4 + A.n_items * 9 + A.n_kept * 4;
+  if (attach_g32(ix.get())) { for (void* d : ix->dev_allocs) cudaFree(d); return nullptr; }
   return ix.release();
+}
+
+int attach_g32(vmis_index* ix) {
+  void* d = nullptr;
+  const size_t n = ix->view.n_items;
+  CU_TRY(cudaMalloc(&d, std::max<size_t>(n * sizeof(float), 16)));
+  ix->dev_allocs.push_back(d);
+  ix->device_bytes += n * sizeof(float);
+  CU_TRY(vmis::build_g32(ix->view.idf, static_cast<float*>(d), (uint32_t)n, nullptr));
+  CU_TRY(cudaDeviceSynchronize());
+  ix->view.g32 = static_cast<const float*>(d);
+  return VMIS_OK;
 }
 
 // borrow a call context; its previous work (possibly on a caller stream) is ordered before ours
@@ -604,6 +621,7 @@ vmis_index_t* vmis_index_load(const char* path, int device) {
   V.post_shard[h.shard] = own_dev; V.n_shards = h.n_shards;
   V.item_hash_mask = (uint32_t)(h.hash_cap - 1); V.n_items = (uint32_t)h.n_items; V.n_kept = (uint32_t)h.n_kept;
   V.m_build = h.m_build; V.m_carry = h.m_carry; V.max_len = h.max_len;
+  if (attach_g32(ix.get())) { for (void* d : ix->dev_allocs) cudaFree(d); return nullptr; }
   ix->n_post_entries = h.n_post_entries; ix->n_sess_item_entries = h.n_sess_item_entries;
   std::vector<uint32_t>().swap(F.sess_items); std::vector<uint2>().swap(F.sess_ref); std::vector<uint2>().swap(F.post_ref);
   return ix.release();

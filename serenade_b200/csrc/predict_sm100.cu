@@ -183,6 +183,8 @@ struct SmemLayout {
   uint32_t overflow;                 // shared table over its occupancy budget → redo on the global table
   uint32_t sel_ok, sel_count;
   uint32_t bound[kWarps];            // per-warp lower bounds of the n-th best coarse score
+  alignas(16) uint32_t top4[kWarps][4];   // phase 3: the four best thread candidates of every warp
+  uint32_t qcount;                   // phase 3: entries in the block-wide candidate queue
   unsigned long long bar[2];         // mbarriers of the two posting-list staging buffers (TMA bulk copies)
 };
 // Scratch that aliases the neighbour arrays (dead or not yet written when it is live): the per-warp numerator
@@ -190,14 +192,20 @@ struct SmemLayout {
 union Scratch {
   uint32_t hist[kWarps][32];
   struct { uint64_t s[kWarps * 32]; uint32_t id[kWarps * 32]; } top;      // exact path: per-warp top-32 lists
-  struct { uint32_t top32[kWarps * 32]; uint32_t queue[kWarps][64]; } sel;
 };
+constexpr uint32_t kSelQ = 1024;     // block-wide queue of top-n candidates (phase 3); more: exact scan
 
-// bytes of the neighbour arrays (4 x K + 1 words), never smaller than the scratch that aliases them
+// bytes of the neighbour arrays (3 x K + 1 words), never smaller than the scratch that aliases them
 __host__ __device__ constexpr size_t nbr_bytes_min() { return sizeof(Scratch); }
 __host__ __device__ inline size_t nbr_bytes(uint32_t k) {
-  size_t b = (size_t(k) * 4 + 1) * 4;
+  size_t b = (size_t(k) * 3 + 1) * 4;
   if (b < nbr_bytes_min()) b = nbr_bytes_min();
+  return (b + 15) & ~size_t(15);
+}
+// bytes of the granule -> neighbour map, never smaller than the per-warp candidate queues of phase 3 that alias it
+__host__ __device__ inline size_t gran_bytes(uint32_t gran_cap) {
+  size_t b = size_t(gran_cap) * 2;
+  if (b < size_t(kSelQ) * 4) b = size_t(kSelQ) * 4;
   return (b + 15) & ~size_t(15);
 }
 
@@ -219,101 +227,125 @@ __device__ __forceinline__ int32_t session_weight10(uint32_t low) {
   return w10 * (int32_t)(low & kNumMask);
 }
 
+// ---- score table: open addressing, one 64-bit slot {item : 32 | A : 32} per item, all ones = empty.  A claim is ONE
+// 64-bit compare-and-swap that deposits key and first weight together; a later hit adds to the low word.
+typedef unsigned long long Slot;
+constexpr Slot kEmptySlot = ~0ull;
+__device__ __forceinline__ uint32_t slot_key(Slot s) { return (uint32_t)(s >> 32); }
+__device__ __forceinline__ int32_t slot_val(Slot s) { return (int32_t)(uint32_t)s; }
+
+__device__ __forceinline__ Slot make_slot(uint32_t item, int32_t w) { return ((Slot)item << 32) | (uint32_t)w; }
+__device__ __forceinline__ uint32_t hash_slot(uint32_t item) { return (item * 0x9E3779B1u) >> 7; }
+__device__ __forceinline__ uint32_t hash_stride(uint32_t item) { return ((item * 0x9E3779B1u) >> 20) | 1u; }
+
 // phase 2b: A[item] += w for every item of every neighbour session (mod.rs:144-153).
 //
-// The neighbours' item lists are walked as ONE flat array of `total` entries, 32 consecutive entries per warp
-// round, so every lane always has exactly one item.  The entry → neighbour map costs two broadcast loads: a
-// bitmap of list starts (fbits) and, per 32-entry word, the neighbour that owns its first entry (fdir); the
-// lane's neighbour is fdir + popcount of the starts up to its bit.  Inserts use double hashing with persistent
-// lanes (see accumulate()).
-// The most recent item of the evolving session is never inserted: it is dropped from the result anyway
-// (mod.rs:157-160) and would be the hottest slot of the table.
-struct FlatMap {
-  const uint32_t* bits;     // [words] bit b of word w: entry 32w+b starts a neighbour's list
-  const uint16_t* dir;      // [words] neighbour owning entry 32w
-  const uint64_t* delta;    // [nn]    (item list offset in sess_items) - (first flat entry): item of entry e = sess_items[delta + e]
-  const uint32_t* w;        // [nn]    weight 10*linear_score*numerator
-};
-
-// Returns the number of slots this WARP claimed; when kRecord, their indices are appended to the warp's own
-// segment `occ_seg` (phase 3 lets every warp score the slots it claimed, so no compaction pass is needed).
-//
-// Lanes are PERSISTENT: every warp owns a contiguous share of the flat entry array; a lane whose insert has
-// finished takes its prefetched next entry and prefetches another one (entries are dealt to the free lanes by
-// a ballot rank), a lane whose probe hit a foreign key just steps on.  Each loop iteration is therefore one
-// probe step of (nearly) 32 live inserts — a round-synchronous loop would idle ~27 lanes while the slowest
-// insert of the round walks its probe sequence (measured: 3.1 iterations per 32 entries at 5 live lanes).
-template <bool kRecord>
-__device__ __forceinline__ uint32_t accumulate(const IndexView& ix, SmemLayout& S, const FlatMap fm, uint32_t total,
-                                               uint32_t last_idx, uint32_t* keys, int32_t* vals, uint32_t mask,
-                                               uint16_t* occ_seg, uint32_t seg_cap) {
-  const uint32_t lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
-  const uint32_t lt_mask = (1u << lane) - 1u;
-  const uint32_t n32 = (total + 31u) >> 5;
-  uint32_t cur_e = ((n32 * warp) / kWarps) << 5;                       // next entry of this warp's share to deal out
-  const uint32_t end_e = min(((n32 * (warp + 1u)) / kWarps) << 5, total);
-  auto gather = [&](uint32_t e, uint32_t& item, int32_t& wgt) {
-    item = kEmpty; wgt = 0;
-    if (e < end_e) {
-      const uint32_t word = e >> 5, b = fm.bits[word];
-      const uint32_t i = (uint32_t)fm.dir[word] + (uint32_t)__popc(b & (0xFFFFFFFFu >> (31u - (e & 31u)))) - (b & 1u);
-      item = __ldg(ix.sess_items + (fm.delta[i] + e));
-      wgt = (int32_t)fm.w[i];
-    }
-  };
-  uint32_t wn = 0;                                   // warp-uniform count of claimed slots
-  uint32_t item = kEmpty, h = 0, stride = 0; int32_t w = 0;
-  uint32_t nitem; int32_t nw;                        // prefetched entry of the lane (not looked at until promoted)
-  gather(cur_e + lane, nitem, nw);
-  cur_e += 32u;
-  bool done = true;
-  const uint32_t seg_last = seg_cap - 1u;
-  bool finished = false;
-  for (uint32_t budget = total + 8192u; budget != 0u; --budget) {     // the budget is unreachable while the table has free slots
-    const uint32_t dm = __ballot_sync(kFull, done);
-    if (done) {
-      item = nitem; w = nw;
-      if (item == last_idx) item = kEmpty;           // dropped from the result anyway (mod.rs:157-160)
-      // double hashing: an odd stride visits every slot of the power-of-two table and avoids the primary
-      // clustering of linear probing (shared memory has no locality to lose)
-      const uint32_t hv = item * 0x9E3779B1u;
-      stride = ((hv >> 20) | 1u) & mask;
-      h = (hv >> 7) & mask;
-      done = item == kEmpty;
-      gather(cur_e + (uint32_t)__popc(dm & lt_mask), nitem, nw);
-    }
-    cur_e += (uint32_t)__popc(dm);
-    if (dm == kFull && !__any_sync(kFull, !done)) {                    // every lane was idle and none got a live entry
-      if (!__any_sync(kFull, nitem != kEmpty)) { finished = true; break; }   // ... and nothing is prefetched
-      continue;
-    }
-    bool claimed = false;
-    if (!done) {
-      uint32_t cur = *reinterpret_cast<volatile uint32_t*>(&keys[h]);
-      if (cur == kEmpty) {
-        cur = atomicCAS(&keys[h], kEmpty, item);
-        if (cur == kEmpty) { claimed = true; cur = item; }
-      }
-      if (cur == item) { atomicAdd(&vals[h], w); done = true; }
-      else h = (h + stride) & mask;
-    }
-    if (kRecord) {
-      const uint32_t cm = __ballot_sync(kFull, claimed);
-      if (cm) {                                      // h still addresses the slot the lane landed on
-        if (claimed) occ_seg[min(wn + (uint32_t)__popc(cm & lt_mask), seg_last)] = (uint16_t)h;
-        wn += (uint32_t)__popc(cm);
-        if (wn > seg_cap) break;                     // over budget: the query is redone on the global table
+// The unit of work is one 16-byte GRANULE of a neighbour's item list (lists start 16-byte aligned and are padded with
+// kEmpty): one LDG.128 brings up to four items that share one weight.  insert_granule() is warp-wide, one granule per
+// lane:
+//   1. the FIRST probe of all four items is straight-line code — four independent 64-bit compare-and-swaps in flight
+//      per lane, no loop, no vote; a claim deposits key and weight at once, a hit adds to the low word (~80 % of the
+//      items are placed here at the table's load factors)
+//   2. the items whose first probe hit a foreign key are finished by a short divergent loop (double hashing: an odd
+//      stride visits every slot of the power-of-two table and avoids the primary clustering of linear probing)
+// No bookkeeping of claimed slots: phase 3 scans the table.  The most recent item of the evolving session is never
+// inserted: it is dropped from the result anyway (mod.rs:157-160) and would be the hottest slot of the table.
+// `nclaim` counts the slots this lane claimed; S.overflow is raised if a probe sequence wrapped (full table).
+__device__ __forceinline__ void insert_granule(SmemLayout& S, const uint4 it, int32_t w, uint32_t last_idx, Slot* tab,
+                                               uint32_t mask, uint32_t& nclaim) {
+  // stage A: four independent compare-and-swaps in flight (no result is looked at before all are issued)
+  const bool v0 = it.x != kEmpty && it.x != last_idx, v1 = it.y != kEmpty && it.y != last_idx;
+  const bool v2 = it.z != kEmpty && it.z != last_idx, v3 = it.w != kEmpty && it.w != last_idx;
+  const uint32_t h0 = hash_slot(it.x) & mask, h1 = hash_slot(it.y) & mask, h2 = hash_slot(it.z) & mask, h3 = hash_slot(it.w) & mask;
+  Slot o0 = 0, o1 = 0, o2 = 0, o3 = 0;                   // key 0 of an unissued probe is never looked at
+  if (v0) o0 = atomicCAS(&tab[h0], kEmptySlot, make_slot(it.x, w));
+  if (v1) o1 = atomicCAS(&tab[h1], kEmptySlot, make_slot(it.y, w));
+  if (v2) o2 = atomicCAS(&tab[h2], kEmptySlot, make_slot(it.z, w));
+  if (v3) o3 = atomicCAS(&tab[h3], kEmptySlot, make_slot(it.w, w));
+  // stage B: a claim is done, a hit adds to the low word (little endian: low word = A), the rest goes on probing
+  const uint32_t k0 = slot_key(o0), k1 = slot_key(o1), k2 = slot_key(o2), k3 = slot_key(o3);
+  if (v0 && k0 == it.x) atomicAdd(reinterpret_cast<int*>(&tab[h0]), w);
+  if (v1 && k1 == it.y) atomicAdd(reinterpret_cast<int*>(&tab[h1]), w);
+  if (v2 && k2 == it.z) atomicAdd(reinterpret_cast<int*>(&tab[h2]), w);
+  if (v3 && k3 == it.w) atomicAdd(reinterpret_cast<int*>(&tab[h3]), w);
+  nclaim += (uint32_t)(v0 && k0 == kEmpty) + (uint32_t)(v1 && k1 == kEmpty) + (uint32_t)(v2 && k2 == kEmpty) + (uint32_t)(v3 && k3 == kEmpty);
+  uint32_t pend = (v0 && k0 != kEmpty && k0 != it.x ? 1u : 0u) | (v1 && k1 != kEmpty && k1 != it.y ? 2u : 0u) |
+                  (v2 && k2 != kEmpty && k2 != it.z ? 4u : 0u) | (v3 && k3 != kEmpty && k3 != it.w ? 8u : 0u);
+  while (__any_sync(kFull, pend != 0u)) {
+    if (pend != 0u) {
+      const uint32_t item = (pend & 1u) ? it.x : (pend & 2u) ? it.y : (pend & 4u) ? it.z : it.w;
+      pend &= pend - 1u;
+      const uint32_t stride = hash_stride(item);
+      uint32_t h = hash_slot(item);
+      uint32_t tries = mask;                             // every other slot once
+      for (;;) {
+        h = (h + stride) & mask;
+        const uint32_t ok = slot_key(atomicCAS(&tab[h], kEmptySlot, make_slot(item, w)));
+        if (ok == kEmpty) { ++nclaim; break; }
+        if (ok == item) { atomicAdd(reinterpret_cast<int*>(&tab[h]), w); break; }
+        if (--tries == 0u) { S.overflow = 1u; break; }   // unreachable while the table has a free slot
       }
     }
   }
-  if ((kRecord && wn > seg_cap) || !finished) S.overflow = 1u;           // over budget, or the probe guard ran out
-  return min(wn, seg_cap);
+}
+
+// Walks the item lists of the nn neighbours into the table.  kFlat: phase 2a flattened the lists into G granules with
+// a granule -> neighbour map (one granule per lane, rounds of 256 granules per block); otherwise (the map did not fit:
+// very long sessions) every warp takes whole neighbours and its lanes stride over that neighbour's granules.
+// With `guard` (the neighbours hold more items than the table's occupancy budget) every warp publishes its claims
+// after each round and stops once the budget is exceeded; the query is then redone on the global table.
+struct NeighbourLists {
+  const uint32_t* goff;      // [nn] kFlat: (item list offset in 16-byte units) - (first granule); else the plain offset
+  const uint32_t* len;       // [nn] item list length
+  const int32_t* w;          // [nn] weight 10*linear_score*numerator
+  const uint16_t* gran_nbr;  // [G]  kFlat: neighbour owning the granule
+};
+template <bool kFlat>
+__device__ __forceinline__ void accumulate(const IndexView& ix, SmemLayout& S, const NeighbourLists nl, uint32_t nn, uint32_t G,
+                                           uint32_t last_idx, Slot* tab, uint32_t mask, bool guard, uint32_t occ_cap) {
+  const uint32_t lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
+  const uint4* lists = reinterpret_cast<const uint4*>(ix.sess_items);
+  const uint4 none = make_uint4(kEmpty, kEmpty, kEmpty, kEmpty);
+  uint32_t nclaim = 0;
+  auto over_budget = [&]() -> bool {                    // warp-uniform; only called with guard
+    const uint32_t c = __reduce_add_sync(kFull, nclaim);
+    nclaim = 0;
+    uint32_t tot = 0;
+    if (lane == 0) tot = atomicAdd(&S.n_occ, c) + c;
+    return __shfl_sync(kFull, tot, 0) > occ_cap;
+  };
+  if (kFlat) {
+    auto fetch = [&](uint32_t g, uint4& it, int32_t& w) {
+      it = none; w = 0;
+      if (g < G) { const uint32_t i = nl.gran_nbr[g]; w = nl.w[i]; it = __ldg(lists + (nl.goff[i] + g)); }
+    };
+    uint4 it; int32_t w;
+    fetch(warp * 32u + lane, it, w);
+    for (uint32_t base = warp * 32u; base < G; base += kThreads) {
+      uint4 nit; int32_t nw;                            // next round's granule travels while this one is inserted
+      fetch(base + kThreads + lane, nit, nw);
+      insert_granule(S, it, w, last_idx, tab, mask, nclaim);
+      if (guard && over_budget()) break;
+      it = nit; w = nw;
+    }
+  } else {
+    bool stop = false;
+    for (uint32_t i = warp; i < nn && !stop; i += kWarps) {
+      const uint32_t ng = (nl.len[i] + 3u) >> 2;
+      const int32_t w = nl.w[i];
+      const uint4* p = lists + nl.goff[i];
+      for (uint32_t g0 = 0; g0 < ng && !stop; g0 += 32u) {
+        insert_granule(S, g0 + lane < ng ? __ldg(p + g0 + lane) : none, w, last_idx, tab, mask, nclaim);
+        if (guard && over_budget()) stop = true;
+      }
+    }
+  }
 }
 
 // compaction of the occupied slots into `occ` (any order): every thread inspects the slots tid, tid+256, ...
 // (coalesced), one block scan places its finds.  Result count in S.n_occ; sets S.overflow if the list is too small.
 template <typename OccT>
-__device__ __forceinline__ void compact_slots(SmemLayout& S, uint32_t& par, const uint32_t* keys, uint32_t cap, OccT* occ,
+__device__ __forceinline__ void compact_slots(SmemLayout& S, uint32_t& par, const Slot* tab, uint32_t cap, OccT* occ,
                                               uint32_t occ_cap) {
   const uint32_t tid = threadIdx.x;
   uint32_t run_total = 0;
@@ -322,7 +354,7 @@ __device__ __forceinline__ void compact_slots(SmemLayout& S, uint32_t& par, cons
 #pragma unroll 8
     for (uint32_t j = 0; j < 32; ++j) {
       const uint32_t slot = chunk + j * kThreads + tid;
-      if (slot < cap && keys[slot] != kEmpty) used |= 1u << j;
+      if (slot < cap && slot_key(tab[slot]) != kEmpty) used |= 1u << j;
     }
     int total;
     uint32_t pos = run_total + (uint32_t)block_excl_scan(__popc(used), S.scan, par, total);
@@ -371,120 +403,27 @@ __device__ __forceinline__ Elem exact_elem(const IndexView& ix, const PredictArg
   return e;
 }
 
-// phase 3: top-n by (score desc, item asc).  Fast path: a monotone 19-bit coarse key (fp32 image of the score)
-// packed with the entry index selects 32 candidates with a u32 warp-bitonic network; if that candidate set
-// provably contains the exact top-n (no coarse tie across its boundary) they are scored exactly and sorted
-// once.  Otherwise (how_many > 31, heavy ties, global table) the exact 96-bit network scans everything.
-// The occupied-slot list `occ` is walked per warp: entries e = e_begin + lane, + e_step, ... < e_end (shared table:
-// the warp's own segment of claimed slots; global table: the compacted list, strided over the warps).
-template <bool kGlobal, typename OccT>
-__device__ __forceinline__ uint32_t select_topn(const IndexView& ix, const PredictArgs& a, SmemLayout& S, Scratch& X,
-                                                const QueryCtx& c, const uint32_t* keys, const int32_t* vals,
-                                                const OccT* occ, uint32_t e_begin, uint32_t e_end, uint32_t e_step) {
+// phase 3, exact path: top-n by (score desc, item asc) with the exact 96-bit (f64 score bits, dense idx) network,
+// rounds of 32 over every entry.  Used when how_many > 31, when the coarse pass could not prove its candidate set
+// (heavy score ties) and for the global table.  Entries: kIdentity — every slot of the shared table (empty slots
+// yield sentinels); otherwise the compacted occupied-slot list `occ` of the global table.
+template <bool kIdentity, typename OccT>
+__device__ __forceinline__ uint32_t select_exact(const IndexView& ix, const PredictArgs& a, SmemLayout& S, Scratch& X,
+                                                 const QueryCtx& c, const Slot* tab, const OccT* occ, uint32_t n_entries) {
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const uint32_t N = a.how_many, q = c.q;
   const double denom = (double)(10u * c.u);
-  const uint32_t n_occ = e_end;                                            // bound of valid entry indices for this warp
-  if (!kGlobal && N <= 31) {
-    // coarse key of entry e (0 = filtered / out of range): 19-bit monotone image of an fp32 APPROXIMATION of the
-    // score (relative error < 2^-21, far below the 2^-10 coarse unit), so exact order can only disagree with
-    // coarse order by one unit: every exact top-n element has coarse >= (n-th largest coarse) - 1.
-    const float rdenom = 1.0f / (float)denom;
-    auto coarse = [&](uint32_t e) -> uint32_t {
-      if (e >= n_occ) return 0u;
-      const uint32_t slot = occ[e];
-      const uint32_t key = keys[slot];
-      if (key == c.last_idx) return 0u;                                    // mod.rs:157-160
-      if (a.biz && !passes_business_rules(c.cur_attr, ix.attr[key])) return 0u;
-      const double idf = ix.idf[key];
-      const float g = idf > 0.0 ? (float)idf : 1.0f;                       // mod.rs:145-152
-      const uint32_t fb = __float_as_uint((float)vals[slot] * g * rdenom);
-      const uint32_t mono = (fb >> 31) ? ~fb : (fb | 0x80000000u);
-      return (mono & ~kIdxMask) | e;
-    };
-    // round 0: every warp sorts its first 32 entries; its N-th best is a lower bound of the global N-th best
-    uint32_t best = u32_sort_desc(coarse(e_begin + lane), lane);
-    if (lane == 0) S.bound[warp] = __shfl_sync(kFull, best, (int)N - 1) >> kIdxBits;
-    else (void)__shfl_sync(kFull, best, (int)N - 1);
-    __syncthreads();
-    uint32_t bound = 0;
-#pragma unroll
-    for (int w = 0; w < kWarps; ++w) bound = max(bound, S.bound[w]);
-    // later rounds: only entries at or above the bound can matter; they are queued and merged 32 at a time
-    uint32_t* queue = X.sel.queue[warp];
-    uint32_t qn = 0;
-    for (uint32_t base = e_begin + e_step; base < e_end; base += e_step) {
-      const uint32_t cand = coarse(base + lane);
-      const bool keep = cand != 0 && (cand >> kIdxBits) + 1u >= bound;
-      const uint32_t km = __ballot_sync(kFull, keep);
-      if (km) {
-        if (keep) queue[qn + __popc(km & ((1u << lane) - 1u))] = cand;
-        qn += __popc(km);
-        __syncwarp();
-        if (qn >= 32) {
-          best = u32_merge_top(best, u32_sort_desc(queue[lane], lane), lane);
-          const uint32_t rest = (uint32_t)lane < qn - 32 ? queue[32 + lane] : 0u;
-          __syncwarp();
-          queue[lane] = rest;
-          qn -= 32;
-          __syncwarp();
-          // the warp's own N-th best so far is also a lower bound of the global N-th best: prune harder from here on
-          bound = max(bound, __shfl_sync(kFull, best, (int)N - 1) >> kIdxBits);
-        }
-      }
-    }
-    if (qn > 0) best = u32_merge_top(best, u32_sort_desc((uint32_t)lane < qn ? queue[lane] : 0u, lane), lane);
-    uint32_t* buf = X.sel.top32;
-    buf[warp * 32 + lane] = best;
-    __syncthreads();
-    if (warp == 0) {
-      // tree merge of the per-warp lists: the merges of one level are independent (shuffle latencies overlap)
-      uint32_t lists[kWarps];
-#pragma unroll
-      for (int w = 0; w < kWarps; ++w) lists[w] = buf[w * 32 + lane];
-#pragma unroll
-      for (int st = 1; st < kWarps; st <<= 1) {
-#pragma unroll
-        for (int w = 0; w + st < kWarps; w += 2 * st) lists[w] = u32_merge_top(lists[w], lists[w + st], lane);
-      }
-      best = lists[0];
-      const uint32_t valid = __popc(__ballot_sync(kFull, best != 0));
-      const uint32_t take = min(valid, N);
-      bool ok = valid < 32;
-      if (!ok) ok = (__shfl_sync(kFull, best, 31) >> kIdxBits) + 1u < (__shfl_sync(kFull, best, (int)N - 1) >> kIdxBits);
-      if (ok) {
-        Elem x; x.s = 0; x.id = kEmpty;
-        if (best != 0) {
-          const uint32_t slot = occ[best & kIdxMask], key = keys[slot];
-          // the external id is read after the sort: start pulling its line now
-          asm volatile("prefetch.global.L2 [%0];" ::"l"(ix.item_key + key));
-          x = exact_elem(ix, a, c, key, vals[slot], denom);
-        }
-        x = warp_sort_desc(x, lane);
-        if ((uint32_t)lane < take) {
-          a.out_ids[(size_t)q * N + lane] = ix.item_key[x.id];
-          a.out_scores[(size_t)q * N + lane] = bits_score(x.s);
-        }
-      }
-      if (lane == 0) { S.sel_ok = ok ? 1u : 0u; S.sel_count = take; }
-    }
-    __syncthreads();
-    const uint32_t ok = S.sel_ok, cnt = S.sel_count;
-    __syncthreads();
-    if (ok) return cnt;
-  }
-  // exact path: rounds of 32 over every occupied slot
   uint32_t written = 0;
   Elem bound; bound.s = ~0ull; bound.id = 0;                      // exclusive upper bound of the current round
   bool first_round = true;
   while (written < N) {
     Elem top; top.s = 0; top.id = kEmpty;
-    for (uint32_t base = e_begin; base < e_end; base += e_step) {
+    for (uint32_t base = (uint32_t)warp * 32u; base < n_entries; base += kThreads) {
       const uint32_t e = base + lane;
       Elem x; x.s = 0; x.id = kEmpty;
-      if (e < e_end) {
-        const uint32_t slot = occ[e];
-        x = exact_elem(ix, a, c, keys[slot], vals[slot], denom);
+      if (e < n_entries) {
+        const Slot sl = tab[kIdentity ? e : (uint32_t)occ[e]];
+        x = exact_elem(ix, a, c, slot_key(sl), slot_val(sl), denom);
         if (!first_round && !better(bound, x)) { x.s = 0; x.id = kEmpty; }
       }
       const Elem worst = shfl_elem(top, 31);
@@ -518,6 +457,124 @@ __device__ __forceinline__ uint32_t select_topn(const IndexView& ix, const Predi
   return written;
 }
 
+// phase 3 on the shared table: top-n by (score desc, item asc) straight from the table, no list of occupied slots
+// and as few dependent steps as possible.
+//
+// A monotone 19-bit coarse key (fp32 image of the score: A * g32[item] / (10 u)) packed with the slot index stands
+// for a slot; exact order can only disagree with coarse order by one coarse unit.
+//   1. every thread owns 16 slots per 4096 (16-byte reads, conflict free) and scores them with all its 4-byte gathers
+//      in flight at once; the keys stay in registers
+//   2. the four best thread maxima of every warp (four REDUX steps) go to shared memory; after one barrier every warp
+//      sorts these 32 keys: their N-th largest is a lower bound B of the query's N-th best key — close to the true
+//      one, because the best items mostly sit with different threads
+//   3. every key reaching B minus one unit goes to ONE block-wide queue (warp scan + one shared atomic per warp);
+//      typically a few more than N survive
+//   4. warp 0: up to 32 survivors are rescored exactly (f64 g(idf) * A / (10 u)) and sorted once with the 96-bit
+//      network; more than 32 are first cut to the 32 best coarse keys, with the margin test proving that cut; if it
+//      cannot (heavy score ties) or the queue overflowed, select_exact() scans the table.
+__device__ __forceinline__ uint32_t select_table(const IndexView& ix, const PredictArgs& a, SmemLayout& S, Scratch& X,
+                                                 uint32_t* queue, const QueryCtx& c, const Slot* tab, uint32_t tab_cap) {
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const uint32_t N = a.how_many, q = c.q;
+  const double denom = (double)(10u * c.u);
+  if (N <= 31) {
+    // coarse key of a slot (0 = empty / filtered): 19-bit monotone image of an fp32 APPROXIMATION of the score
+    // (relative error < 2^-21, far below the 2^-10 coarse unit): every exact top-n element has coarse >= (n-th largest
+    // coarse) - 1.  The current item is never in the table (accumulate drops it, mod.rs:157-160).
+    const float rdenom = 1.0f / (float)denom;
+    auto coarse = [&](uint32_t slot, uint32_t key, uint32_t A) -> uint32_t {
+      bool valid = key != kEmpty;
+      float g = 0.0f;
+      if (valid) g = __ldg(ix.g32 + key);                                  // mod.rs:145-152
+      if (a.biz) { if (valid && !passes_business_rules(c.cur_attr, ix.attr[key])) valid = false; }
+      const uint32_t fb = __float_as_uint((float)(int32_t)A * g * rdenom);
+      const uint32_t mono = fb ^ ((uint32_t)((int32_t)fb >> 31) | 0x80000000u);
+      return valid ? ((mono & ~kIdxMask) | slot) : 0u;
+    };
+    const uint4* t2 = reinterpret_cast<const uint4*>(tab);                 // {A0, key0, A1, key1}
+    const uint32_t passes = tab_cap / (16u * kThreads);                    // tab_cap is a multiple of 4096
+    uint32_t thr = 1u;                                                     // keys at or above stay in the race
+    if (tid == 0) S.qcount = 0;
+    for (uint32_t ps = 0; ps < passes; ++ps) {
+      uint32_t cc[16];
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        const uint32_t p = (ps * 8u + (uint32_t)j) * kThreads + (uint32_t)tid;
+        const uint4 u = t2[p];
+        cc[2 * j] = coarse(2u * p, u.y, u.x);
+        cc[2 * j + 1] = coarse(2u * p + 1u, u.w, u.z);
+      }
+      if (ps == 0) {
+        uint32_t m = cc[0];
+#pragma unroll
+        for (int j = 1; j < 16; ++j) m = max(m, cc[j]);
+        // the warp's four best thread maxima (keys are unique: they carry the slot)
+        const uint32_t t0 = __reduce_max_sync(kFull, m); if (m == t0) m = 0u;
+        const uint32_t t1 = __reduce_max_sync(kFull, m); if (m == t1) m = 0u;
+        const uint32_t t2_ = __reduce_max_sync(kFull, m); if (m == t2_) m = 0u;
+        const uint32_t t3 = __reduce_max_sync(kFull, m);
+        if (lane == 0) *reinterpret_cast<uint4*>(S.top4[warp]) = make_uint4(t0, t1, t2_, t3);
+        __syncthreads();
+        const uint32_t s32 = u32_sort_desc((lane >> 2) < kWarps ? S.top4[lane >> 2][lane & 3] : 0u, lane);
+        const uint32_t bound = __shfl_sync(kFull, s32, (int)N - 1) >> kIdxBits;   // 0: fewer than N candidates so far
+        thr = bound > 1u ? (bound - 1u) << kIdxBits : 1u;
+      }
+      uint32_t keep = 0;
+#pragma unroll
+      for (int j = 0; j < 16; ++j) keep |= (cc[j] >= thr ? 1u : 0u) << j;
+      if (__any_sync(kFull, keep != 0u)) {
+        const int cnt = __popc(keep);
+        const int incl = warp_incl_scan(cnt, lane);
+        uint32_t base = 0;
+        if (lane == 31) base = atomicAdd(&S.qcount, (uint32_t)incl);
+        uint32_t pos = __shfl_sync(kFull, base, 31) + (uint32_t)(incl - cnt);
+#pragma unroll
+        for (int j = 0; j < 16; ++j) {
+          if ((keep >> j) & 1u) { if (pos < kSelQ) queue[pos] = cc[j]; ++pos; }
+        }
+      }
+    }
+    __syncthreads();
+    if (warp == 0) {
+      const uint32_t n = S.qcount;
+      bool ok = n <= kSelQ;
+      uint32_t best = 0;
+      if (ok) {
+        if (n <= 32u) {
+          best = (uint32_t)lane < n ? queue[lane] : 0u;
+        } else {
+          // cut to the 32 best coarse keys; the cut is proven if the last one is more than a unit below the N-th
+          for (uint32_t b = 0; b < n; b += 32u)
+            best = u32_merge_top(best, u32_sort_desc(b + lane < n ? queue[b + lane] : 0u, lane), lane);
+          ok = (__shfl_sync(kFull, best, 31) >> kIdxBits) + 1u < (__shfl_sync(kFull, best, (int)N - 1) >> kIdxBits);
+        }
+      }
+      const uint32_t valid = __popc(__ballot_sync(kFull, best != 0));
+      const uint32_t take = min(valid, N);
+      if (ok) {
+        Elem x; x.s = 0; x.id = kEmpty;
+        if (best != 0) {
+          const Slot sl = tab[best & kIdxMask];
+          // the external id is read after the sort: start pulling its line now
+          asm volatile("prefetch.global.L2 [%0];" ::"l"(ix.item_key + slot_key(sl)));
+          x = exact_elem(ix, a, c, slot_key(sl), slot_val(sl), denom);
+        }
+        x = warp_sort_desc(x, lane);
+        if ((uint32_t)lane < take) {
+          a.out_ids[(size_t)q * N + lane] = ix.item_key[x.id];
+          a.out_scores[(size_t)q * N + lane] = bits_score(x.s);
+        }
+      }
+      if (lane == 0) { S.sel_ok = ok ? 1u : 0u; S.sel_count = take; }
+    }
+    __syncthreads();
+    const uint32_t ok = S.sel_ok, cnt = S.sel_count;
+    __syncthreads();
+    if (ok) return cnt;
+  }
+  return select_exact<true, uint16_t>(ix, a, S, X, c, tab, nullptr, tab_cap);
+}
+
 
 __global__ void __launch_bounds__(kThreads, kCtasPerSm)
 vmis_predict_kernel(const IndexView ix, const PredictArgs a, const LaunchPlan plan, const Workspace ws) {
@@ -526,9 +583,9 @@ vmis_predict_kernel(const IndexView ix, const PredictArgs a, const LaunchPlan pl
   unsigned char* dyn = smem_raw + ((sizeof(SmemLayout) + 15) & ~size_t(15));
   // neighbour arrays
   Scratch& X = *reinterpret_cast<Scratch*>(dyn);
-  uint64_t* nbr_delta = reinterpret_cast<uint64_t*>(dyn);          // [K]   item list offset - first flat entry (phase 2)
-  uint32_t* nbr_sid = reinterpret_cast<uint32_t*>(nbr_delta + a.k);// [K+1] time rank of the neighbour session ...
-  uint32_t* nbr_start = nbr_sid;                                   //       ... later its item list length
+  uint32_t* nbr_goff = reinterpret_cast<uint32_t*>(dyn);           // [K]   item list offset (16-byte units) - first granule (phase 2)
+  uint32_t* nbr_sid = nbr_goff + a.k;                              // [K+1] time rank of the neighbour session ...
+  uint32_t* nbr_len = nbr_sid;                                     //       ... later its item list length
   uint32_t* nbr_low = nbr_sid + a.k + 1;                           // [K]   pos|numerator, later the weight w
   unsigned char* region = dyn + nbr_bytes(a.k);
   // phase-0 view of the region
@@ -538,11 +595,8 @@ vmis_predict_kernel(const IndexView ix, const PredictArgs a, const LaunchPlan pl
   uint64_t* acc1 = acc0 + plan.m_eff;
   uint32_t* listbuf = reinterpret_cast<uint32_t*>(acc1 + plan.m_eff);
   // phase-2/3 view of the region (aliases phase 1)
-  uint32_t* stab_keys = reinterpret_cast<uint32_t*>(region);
-  int32_t* stab_vals = reinterpret_cast<int32_t*>(stab_keys + plan.tab_cap);
-  uint32_t* fbits = reinterpret_cast<uint32_t*>(stab_vals + plan.tab_cap);
-  uint16_t* fdir = reinterpret_cast<uint16_t*>(fbits + plan.fmap_words);
-  uint16_t* socc = fdir + plan.fmap_words;                         // kWarps segments of claimed slots
+  Slot* stab = reinterpret_cast<Slot*>(region);                    // score table {item | A}
+  uint16_t* gran_nbr = reinterpret_cast<uint16_t*>(stab + plan.tab_cap);        // granule -> neighbour; phase 3: candidate queues
 
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const uint32_t K = a.k, M = a.m, N = a.how_many;
@@ -570,6 +624,13 @@ vmis_predict_kernel(const IndexView ix, const PredictArgs a, const LaunchPlan pl
     if (q >= a.n_q) break;
     if (tid == 0) next_q = atomicAdd(ws.counter, 1u);
 
+#ifdef VMIS_PHASE_CLOCKS
+    long long clk[6]; int nclk = 0;
+#define VMIS_CLK() do { if (tid == 0 && nclk < 6) clk[nclk++] = clock64(); } while (0)
+#else
+#define VMIS_CLK() do {} while (0)
+#endif
+    VMIS_CLK();
     // ------------------------------------------------------------------ phase 0
     const uint32_t qo = a.q_off[q];
     const uint32_t Lfull = a.q_off[q + 1] - qo;
@@ -605,6 +666,7 @@ vmis_predict_kernel(const IndexView ix, const PredictArgs a, const LaunchPlan pl
     uint32_t nn = 0;                 // number of neighbours
     uint32_t postings_visited = 0;
 
+    VMIS_CLK();
     if (nd > 0 && K > 0 && M > 0 && (N > 0 || neighbors_mode)) {
       // ---------------------------------------------------------------- phase 1
       const uint2 ref0 = ix.post_ref[S.d_idx[0]];
@@ -798,28 +860,25 @@ vmis_predict_kernel(const IndexView ix, const PredictArgs a, const LaunchPlan pl
       continue;
     }
 
+    VMIS_CLK();
     // ------------------------------------------------------------------ phase 2a: neighbour directory
     {
-      // keys and values are adjacent and the capacity is a multiple of 1024: clear both with 16-byte stores
-      uint4* t4 = reinterpret_cast<uint4*>(stab_keys);
-      const uint32_t n4 = plan.tab_cap >> 2;
-      for (uint32_t i = tid; i < n4; i += kThreads) {
-        t4[i] = make_uint4(kEmpty, kEmpty, kEmpty, kEmpty);
-        t4[n4 + i] = make_uint4(0u, 0u, 0u, 0u);
-      }
+      // all ones = empty; the capacity is a multiple of 4096: 16-byte stores
+      uint4* t4 = reinterpret_cast<uint4*>(stab);
+      const uint32_t n4 = plan.tab_cap >> 1;
+      for (uint32_t i = tid; i < n4; i += kThreads) t4[i] = make_uint4(kEmpty, kEmpty, kEmpty, kEmpty);
     }
     if (tid == 0) { S.n_occ = 0; S.overflow = 0; }
-    for (uint32_t i = tid; i < plan.fmap_words; i += kThreads) fbits[i] = 0u;
-    const uint32_t En = (nn + kThreads - 1) / kThreads;             // contiguous neighbours per thread
-    const uint32_t i0 = min((uint32_t)tid * En, nn), i1 = min(i0 + En, nn);
-    int my_len = 0;
-    for (uint32_t i = i0; i < i1; ++i) {
+    // neighbours tid, tid + 256, ...: item list refs, weights, granule counts (the order of the neighbours is free)
+    uint32_t my_g = 0, my_len = 0;
+    for (uint32_t i = tid; i < nn; i += kThreads) {
       const uint2 r = ix.sess_ref[nbr_sid[i]];
-      prefetch_l2(ix.sess_items + (size_t)r.x * 4);                 // the inserts read this list next
-      nbr_delta[i] = (uint64_t)r.x * 4; nbr_start[i] = r.y; my_len += (int)r.y;    // offset and length parked until the scan
+      const uint32_t* items = ix.sess_items + (size_t)r.x * 4;
+      prefetch_l2(items);                                           // the inserts read this list next
+      if (r.y > 4u) prefetch_l2(items + (r.y - 1u));
+      nbr_goff[i] = r.x; nbr_len[i] = r.y; my_g += (r.y + 3u) >> 2; my_len += r.y;
       uint32_t low = nbr_low[i];
       if (!pos_from_lists) {                                        // reference scan (mod.rs:133-138)
-        const uint32_t* items = ix.sess_items + (size_t)r.x * 4;
         uint32_t pmin = 0xFFu;
         for (uint32_t t = 0; t < r.y; ++t) {
           const uint32_t it = items[t];
@@ -829,53 +888,64 @@ vmis_predict_kernel(const IndexView ix, const PredictArgs a, const LaunchPlan pl
       }
       nbr_low[i] = (uint32_t)session_weight10(low);
     }
-    int total_i;
-    uint32_t run = (uint32_t)block_excl_scan(my_len, S.scan, par, total_i);
-    const uint32_t total_items = (uint32_t)total_i;
-    for (uint32_t i = i0; i < i1; ++i) {
-      const uint32_t len = nbr_start[i], last = run + len - 1;
-      nbr_delta[i] -= run;
-      atomicOr(&fbits[run >> 5], 1u << (run & 31u));
-      for (uint32_t wd = (run + 31u) >> 5; wd <= (last >> 5); ++wd) fdir[wd] = (uint16_t)i;
-      run += len;
+    // one packed scan for the granule offsets and the item count (two when the counts may not fit 16 bits each)
+    uint32_t run, G, total_items;
+    if (K * ix.max_len <= 0xFFFFu) {
+      int tot;
+      run = (uint32_t)block_excl_scan((int)(my_g | (my_len << 16)), S.scan, par, tot) & 0xFFFFu;
+      G = (uint32_t)tot & 0xFFFFu; total_items = (uint32_t)tot >> 16;
+    } else {
+      int tot;
+      run = (uint32_t)block_excl_scan((int)my_g, S.scan, par, tot);
+      G = (uint32_t)tot;
+      total_items = (uint32_t)block_sum((int)my_len, S.scan, par);
+    }
+    const bool flat = G <= plan.gran_cap;
+    if (flat) {
+      for (uint32_t i = tid; i < nn; i += kThreads) {
+        const uint32_t ng = (nbr_len[i] + 3u) >> 2;
+        nbr_goff[i] -= run;
+        for (uint32_t g = run; g < run + ng; ++g) gran_nbr[g] = (uint16_t)i;
+        run += ng;
+      }
     }
     __syncthreads();
 
+    VMIS_CLK();
     // ------------------------------------------------------------------ phase 2b + 3
     QueryCtx c;
     c.q = q; c.u = u; c.last_idx = last_idx; c.cur_attr = cur_attr;
     uint32_t written;
     // shared-memory score table first; the rare query whose neighbours hold more distinct items than its
     // occupancy budget is redone on this CTA's global table
-    FlatMap fm;
-    fm.bits = fbits; fm.dir = fdir; fm.delta = nbr_delta; fm.w = nbr_low;
-    // every warp records the slots it claims in its own segment of the list and scores exactly those in phase 3
-    const uint32_t seg = plan.occ_cap / kWarps;
+    NeighbourLists nl;
+    nl.goff = nbr_goff; nl.len = nbr_len; nl.w = reinterpret_cast<const int32_t*>(nbr_low); nl.gran_nbr = gran_nbr;
     if (nn == 0 || N == 0) {
       written = 0;
     } else {
-    const uint32_t wn = accumulate<true>(ix, S, fm, total_items, last_idx, stab_keys, stab_vals, plan.tab_cap - 1,
-                                         socc + (size_t)warp * seg, seg);
-    __syncthreads();
-    if (!S.overflow) {
-      written = select_topn<false, uint16_t>(ix, a, S, X, c, stab_keys, stab_vals, socc, (uint32_t)warp * seg,
-                                             (uint32_t)warp * seg + wn, 32u);
-    } else {
-      // redo on this CTA's global table: big enough for every item of every neighbour, cleaned after use
-      uint32_t* gkeys = ws.gtab_keys + (size_t)blockIdx.x * ws.gtab_cap;
-      int32_t* gvals = ws.gtab_vals + (size_t)blockIdx.x * ws.gtab_cap;
-      uint32_t* gocc = ws.gtab_occ + (size_t)blockIdx.x * (ws.gtab_cap / 2);
+      const bool guard = total_items > plan.occ_cap;                // the neighbours may hold more distinct items than the budget
+      if (flat) accumulate<true>(ix, S, nl, nn, G, last_idx, stab, plan.tab_cap - 1, guard, plan.occ_cap);
+      else accumulate<false>(ix, S, nl, nn, G, last_idx, stab, plan.tab_cap - 1, guard, plan.occ_cap);
       __syncthreads();
-      if (tid == 0) { S.n_occ = 0; S.overflow = 0; }
-      __syncthreads();
-      accumulate<false>(ix, S, fm, total_items, last_idx, gkeys, gvals, ws.gtab_cap - 1, nullptr, 0u);
-      __syncthreads();
-      compact_slots<uint32_t>(S, par, gkeys, ws.gtab_cap, gocc, ws.gtab_cap / 2);
-      __syncthreads();
-      const uint32_t n_occ = S.n_occ;
-      written = select_topn<true, uint32_t>(ix, a, S, X, c, gkeys, gvals, gocc, (uint32_t)warp * 32u, n_occ, kThreads);
-      for (uint32_t e = tid; e < n_occ; e += kThreads) { const uint32_t slot = gocc[e]; gkeys[slot] = kEmpty; gvals[slot] = 0; }
-    }
+      VMIS_CLK();
+      if (!S.overflow && S.n_occ <= plan.occ_cap) {
+        written = select_table(ix, a, S, X, reinterpret_cast<uint32_t*>(gran_nbr), c, stab, plan.tab_cap);
+      } else {
+        // redo on this CTA's global table: big enough for every item of every neighbour, cleaned after use
+        Slot* gtab = ws.gtab + (size_t)blockIdx.x * ws.gtab_cap;
+        uint32_t* gocc = ws.gtab_occ + (size_t)blockIdx.x * (ws.gtab_cap / 2);
+        __syncthreads();
+        if (tid == 0) { S.n_occ = 0; S.overflow = 0; }
+        __syncthreads();
+        if (flat) accumulate<true>(ix, S, nl, nn, G, last_idx, gtab, ws.gtab_cap - 1, false, 0u);
+        else accumulate<false>(ix, S, nl, nn, G, last_idx, gtab, ws.gtab_cap - 1, false, 0u);
+        __syncthreads();
+        compact_slots<uint32_t>(S, par, gtab, ws.gtab_cap, gocc, ws.gtab_cap / 2);
+        __syncthreads();
+        const uint32_t n_occ = S.n_occ;
+        written = select_exact<false, uint32_t>(ix, a, S, X, c, gtab, gocc, n_occ);
+        for (uint32_t e = tid; e < n_occ; e += kThreads) gtab[gocc[e]] = kEmptySlot;
+      }
     }
     for (uint32_t i = written + tid; i < N; i += kThreads) {           // deterministic padding
       a.out_ids[(size_t)q * N + i] = 0; a.out_scores[(size_t)q * N + i] = 0.0;
@@ -885,6 +955,15 @@ vmis_predict_kernel(const IndexView ix, const PredictArgs a, const LaunchPlan pl
       if (a.out_stats) {
         vmis_query_stats_t st; st.postings_visited = postings_visited; st.n_neighbors = nn;
         st.neighbor_items = total_items; st.n_out = written;
+#ifdef VMIS_PHASE_CLOCKS
+        // tuning build: cycles of {phase 0, phases 1 + 1b, phase 2a, phase 2b} instead of the work counters
+        clk[nclk] = clock64();
+        if (nclk == 5) {
+          st.postings_visited = (uint32_t)(clk[1] - clk[0]); st.n_neighbors = (uint32_t)(clk[2] - clk[1]);
+          st.neighbor_items = (uint32_t)(clk[3] - clk[2]); st.n_out = (uint32_t)(clk[4] - clk[3]);
+          a.out_counts[q] = (uint32_t)(clk[5] - clk[4]);           // phase 3
+        }
+#endif
         a.out_stats[q] = st;
       }
     }
@@ -906,24 +985,34 @@ int plan_launch(const IndexView& ix, uint32_t k, uint32_t m, int sm_count, Launc
   // one extra entry each: the merge steps read a sentinel behind both runs
   p.m_eff = (std::max(m, 1u) + 1u + 3u) & ~3u;
   p.list_cap = (std::min(std::max(m, 1u), std::max(ix.m_build, 1u)) + 1u + 3u) & ~3u;
-  uint32_t tab = next_pow2(std::max(k, 1u) * 12u);
-  p.tab_cap = std::min(std::max(tab, 1024u), 8192u);
+  // score table: >= 4096 slots so that the occupancy budget plus one round of inserts (4 items per thread) never
+  // fills it (insert_granule relies on a free slot being reachable)
+  const uint32_t tab = next_pow2(std::max(k, 1u) * 12u);
+  p.tab_cap = std::min(std::max(tab, 4096u), 8192u);
+  p.occ_cap = p.tab_cap / 2 + p.tab_cap / 8;                        // 62.5 % of the slots
   const size_t fixed = (sizeof(SmemLayout) + 15) & ~size_t(15);
   const size_t nbr = nbr_bytes(k);
   const size_t r1 = size_t(p.m_eff) * 16 + size_t(p.list_cap) * 8;   // two m-sample buffers + two TMA staging buffers
-  p.fmap_words = (std::max(k, 1u) * std::max(ix.max_len, 1u) + 31u) / 32u + 1u;
-  if (p.fmap_words > 65535u) return VMIS_ERR_LIMIT;
-  // tail of the table region: the flat map and the per-warp lists of claimed slots (u16)
-  p.occ_cap = (p.tab_cap / 2 + p.tab_cap / 8) / kWarps * kWarps;          // 62.5 % of the slots, split over the warps
-  const size_t r2 = size_t(p.tab_cap) * 8 + size_t(p.fmap_words) * 6 + size_t(p.occ_cap) * 2 + 8;
+  // granule -> neighbour map behind the table: the worst case (every neighbour as long as the longest session) if it
+  // leaves room for the full CTA count, else what fits; queries beyond it walk their neighbours list by list
+  const uint64_t want = (uint64_t)std::max(k, 1u) * ((std::max(ix.max_len, 1u) + 3u) / 4u);
+  const size_t per_cta = (227 * 1024) / kCtasPerSm - 1024;           // 1 KB per CTA is reserved by the driver
+  const size_t base = fixed + nbr + 16 + size_t(p.tab_cap) * 8;
+  uint64_t room = per_cta > base ? (per_cta - base) / 2 : 0;
+  if (fixed + nbr + 16 + r1 > base) room = std::max<uint64_t>(room, (fixed + nbr + 16 + r1 - base) / 2);   // free under phase 1
+  p.gran_cap = (uint32_t)std::min<uint64_t>(want, std::max<uint64_t>(room, 1280));
+  p.gran_cap &= ~7u;
+  const size_t r2 = size_t(p.tab_cap) * 8 + gran_bytes(p.gran_cap);
   const size_t total = fixed + nbr + std::max(std::max(r1, r2), size_t(kMaxSessionLen) * 8) + 16;
   if (total > 227 * 1024) return VMIS_ERR_LIMIT;
   p.smem_bytes = (uint32_t)total;
-  int per_sm = (int)std::min<size_t>(kCtasPerSm, (227 * 1024) / (total + 1024));   // 1 KB per CTA is reserved by the driver
+  int per_sm = (int)std::min<size_t>(kCtasPerSm, (227 * 1024) / (total + 1024));
   if (const char* e = std::getenv("VMIS_CTAS_PER_SM")) per_sm = std::min(per_sm, std::max(1, std::atoi(e)));   // tuning knob
   if (per_sm < 1) per_sm = 1;
   p.grid = (uint32_t)(sm_count * per_sm);
-  p.gtab_cap = next_pow2(std::max(2u * std::max(k, 1u) * std::max(ix.max_len, 1u), 1024u));
+  const uint64_t gt = 2ull * std::max(k, 1u) * std::max(ix.max_len, 1u);
+  if (gt > (1ull << 30)) return VMIS_ERR_LIMIT;
+  p.gtab_cap = next_pow2(std::max<uint32_t>((uint32_t)gt, 1024u));
   *plan = p;
   return VMIS_OK;
 }
@@ -936,8 +1025,7 @@ Workspace carve_workspace(void* base, const LaunchPlan& plan) {
   Workspace ws{};
   unsigned char* b = static_cast<unsigned char*>(base);
   ws.counter = reinterpret_cast<uint32_t*>(b);
-  ws.gtab_keys = reinterpret_cast<uint32_t*>(b + 256);
-  ws.gtab_vals = reinterpret_cast<int32_t*>(b + 256 + size_t(plan.grid) * plan.gtab_cap * 4);
+  ws.gtab = reinterpret_cast<unsigned long long*>(b + 256);
   ws.gtab_occ = reinterpret_cast<uint32_t*>(b + 256 + size_t(plan.grid) * plan.gtab_cap * 8);
   ws.gtab_cap = plan.gtab_cap;
   ws.grid = plan.grid;
@@ -948,9 +1036,20 @@ cudaError_t init_workspace(const Workspace& ws, cudaStream_t stream) {
   const size_t n = size_t(ws.grid) * ws.gtab_cap;
   cudaError_t e = cudaMemsetAsync(ws.counter, 0, 2 * sizeof(uint32_t), stream);   // work counter + exit counter
   if (e != cudaSuccess) return e;
-  e = cudaMemsetAsync(ws.gtab_keys, 0xFF, n * 4, stream);
-  if (e != cudaSuccess) return e;
-  return cudaMemsetAsync(ws.gtab_vals, 0, n * 4, stream);
+  return cudaMemsetAsync(ws.gtab, 0xFF, n * 8, stream);                            // all ones = empty slot
+}
+
+namespace {
+__global__ void g32_kernel(const double* __restrict__ idf, float* __restrict__ g32, uint32_t n) {
+  const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) { const double x = idf[i]; g32[i] = x > 0.0 ? (float)x : 1.0f; }     // mod.rs:145-152
+}
+}  // namespace
+
+cudaError_t build_g32(const double* idf, float* g32, uint32_t n_items, cudaStream_t stream) {
+  if (n_items == 0) return cudaSuccess;
+  g32_kernel<<<(n_items + 255) / 256, 256, 0, stream>>>(idf, g32, n_items);
+  return cudaGetLastError();
 }
 
 cudaError_t launch_predict(const IndexView& ix, const PredictArgs& args, const LaunchPlan& plan, const Workspace& ws,

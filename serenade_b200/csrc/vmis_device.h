@@ -41,7 +41,7 @@ struct alignas(16) ItemHashEntry {
 //                     gather of vmis_index.rs:359: rank order == (ts, session idx) order)
 //   sess_items        per kept session (by time rank): dense item indices ascending,
 //                     list start aligned to 16 B (replaces session_to_items_sorted)
-//   idf[I], attr[I]   item_to_idf_score / item_to_product_attributes
+//   idf[I], attr[I]   item_to_idf_score / item_to_product_attributes; g32[I] fp32 image of the idf weight
 //   rank_to_orig[Sk]  time rank -> reference session index (find_neighbors output only)
 struct IndexView {
   const uint64_t* item_key;
@@ -60,6 +60,7 @@ struct IndexView {
   uint32_t m_build;           // longest posting list (staging capacity)
   uint32_t m_carry;           // m <= m_carry: every session of the m-sample is on the list of each evolving item it holds
   uint32_t max_len;
+  const float* g32;           // g(idf[i]) = (idf > 0 ? (float)idf : 1) as fp32: the coarse pass of the top-n selection reads 4 bytes per item
 };
 
 struct PredictArgs {
@@ -84,8 +85,7 @@ struct PredictArgs {
 // slot is {kEmpty, 0} (init_workspace() establishes it, the kernel restores it).
 struct Workspace {
   uint32_t* counter;          // [0] work counter, [1] exit counter; zero between launches (the last CTA re-arms them)
-  uint32_t* gtab_keys;        // grid × gtab_cap
-  int32_t* gtab_vals;         // grid × gtab_cap
+  unsigned long long* gtab;   // grid × gtab_cap score-table slots {key : 32 | value : 32}, all ones = empty
   uint32_t* gtab_occ;         // grid × gtab_cap / 2: occupied-slot lists
   uint32_t gtab_cap;          // power of two >= 2 * k * max_len
   uint32_t grid;
@@ -96,7 +96,7 @@ struct LaunchPlan {
   uint32_t smem_bytes;
   uint32_t tab_cap;           // shared score table slots (power of two)
   uint32_t occ_cap;           // occupancy budget of the shared table (distinct items)
-  uint32_t fmap_words;        // 32-entry words of the flat neighbour-item map (k * max_len / 32 + 1)
+  uint32_t gran_cap;          // capacity of the flat granule -> neighbour map (16-byte granules of the neighbours' item lists)
   uint32_t m_eff;             // acc buffer capacity
   uint32_t list_cap;          // posting staging capacity
   uint32_t gtab_cap;
@@ -112,6 +112,8 @@ cudaError_t init_workspace(const Workspace& ws, cudaStream_t stream);
 // Enqueues the predict kernel on `stream` (the workspace must have been initialised once).
 cudaError_t launch_predict(const IndexView& ix, const PredictArgs& args, const LaunchPlan& plan, const Workspace& ws,
                            cudaStream_t stream);
+// g32[i] = idf[i] > 0 ? (float)idf[i] : 1 (IndexView::g32), computed on the device from the uploaded idf array
+cudaError_t build_g32(const double* idf, float* g32, uint32_t n_items, cudaStream_t stream);
 // number of kernels launch_predict enqueues (bench "gpu_launches")
 constexpr int kLaunchesPerBatch = 1;
 

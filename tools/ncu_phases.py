@@ -32,9 +32,10 @@ def find(s):
     if s.startswith("phase"):     # code markers look like "// ------ phase 2a: ..."; the header comment also names phases
         return next(i + 1 for i, l in enumerate(src) if re.search(r"// -{10,} " + re.escape(s), l))
     return next(i + 1 for i, l in enumerate(src) if s in l)
-marks = [("helpers (sort/scan/hash)", 1), ("accumulate (phase 2b)", find("struct FlatMap")),
+marks = [("helpers (sort/scan/hash)", 1), ("accumulate (phase 2b)", find("// phase 2b: A[item] += w")), ("compact_slots (global table)", find("// compaction of the occupied slots")),
          ("select helpers (u32 net, exact_elem)", find("constexpr int kIdxBits")),
-         ("select_topn (phase 3)", find("__device__ __forceinline__ uint32_t select_topn")),
+         ("select_exact (phase 3, rare)", find("// phase 3, exact path")),
+         ("select_table (phase 3)", find("// phase 3 on the shared table")),
          ("kernel prologue", find("vmis_predict_kernel(const IndexView")),
          ("phase 0", find("phase 0")), ("phase 1 merge", find("phase 1")), ("phase 1b top-k", find("phase 1b")),
          ("neighbours mode", find("if (neighbors_mode) {")), ("phase 2a directory", find("phase 2a")),
