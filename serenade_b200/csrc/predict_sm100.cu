@@ -102,10 +102,11 @@ __device__ __forceinline__ int warp_incl_scan(int v, int lane) {
   }
   return v;
 }
-// Block-wide exclusive scan with ONE barrier: warp totals go to a double-buffered scratch row and every
-// warp re-scans the kWarps totals itself.  `par` alternates the row; a row is only rewritten two calls
-// later, i.e. after another barrier, so no trailing barrier is needed.  All threads must call.
-struct ScanScratch { int row[2][kWarps]; };
+// Block-wide exclusive scan with ONE barrier: warp totals go to a double-buffered scratch row and every warp adds up
+// the totals of the warps before it (two 16-byte broadcast reads, no second shuffle scan).  `par` alternates the row;
+// a row is only rewritten two calls later, i.e. after another barrier, so no trailing barrier is needed.  All threads
+// must call.
+struct ScanScratch { alignas(16) int row[2][kWarps]; };
 __device__ __forceinline__ int block_excl_scan(int v, ScanScratch& sc, uint32_t& par, int& total) {
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   int* row = sc.row[par & 1u];
@@ -113,10 +114,17 @@ __device__ __forceinline__ int block_excl_scan(int v, ScanScratch& sc, uint32_t&
   const int inc = warp_incl_scan(v, lane);
   if (lane == 31) row[warp] = inc;
   __syncthreads();
-  const int w = lane < kWarps ? row[lane] : 0;
-  const int wi = warp_incl_scan(w, lane);
-  total = __shfl_sync(kFull, wi, kWarps - 1);
-  return __shfl_sync(kFull, wi - w, warp) + inc - v;
+  int before = 0, all = 0;
+  if (kWarps == 8) {
+    const int4 a = *reinterpret_cast<const int4*>(row), b = *reinterpret_cast<const int4*>(row + 4);
+    const int t[8] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w};
+#pragma unroll
+    for (int w = 0; w < 8; ++w) { all += t[w]; if (w < warp) before += t[w]; }
+  } else {
+    for (int w = 0; w < kWarps; ++w) { const int t = row[w]; all += t; if (w < warp) before += t; }
+  }
+  total = all;
+  return before + inc - v;
 }
 __device__ __forceinline__ int block_sum(int v, ScanScratch& sc, uint32_t& par) {
   int total;
@@ -172,7 +180,17 @@ __device__ __forceinline__ void bulk_load(void* dst_smem, const void* src_gmem, 
 __device__ __forceinline__ void prefetch_l2(const void* p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
 __device__ __forceinline__ void fence_async_proxy() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 
+#ifdef VMIS_PHASE_CLOCKS
+#define VMIS_CLK_FIELDS long long clk[16]; uint32_t nclk;
+#define VMIS_CLK_RESET(S) do { (S).nclk = 0; } while (0)
+#define VMIS_CLK(S) do { if (threadIdx.x == 0 && (S).nclk < 16) (S).clk[(S).nclk++] = clock64(); } while (0)
+#else
+#define VMIS_CLK_FIELDS
+#define VMIS_CLK_RESET(S) do {} while (0)
+#define VMIS_CLK(S) do {} while (0)
+#endif
 struct SmemLayout {
+  VMIS_CLK_FIELDS
   // fixed part
   uint32_t d_idx[kMaxSessionLen];    // distinct known items, most recent first
   uint8_t d_pos[kMaxSessionLen];
@@ -180,6 +198,7 @@ struct SmemLayout {
   uint32_t q;                        // current query
   uint32_t nd;
   uint32_t n_occ;                    // occupied score-table slots of the current query
+  uint32_t round;                    // phase 2b: next round of 32 granules to hand to a warp
   uint32_t overflow;                 // shared table over its occupancy budget → redo on the global table
   uint32_t sel_ok, sel_count;
   uint32_t bound[kWarps];            // per-warp lower bounds of the n-th best coarse score
@@ -192,6 +211,7 @@ struct SmemLayout {
 union Scratch {
   uint32_t hist[kWarps][32];
   struct { uint64_t s[kWarps * 32]; uint32_t id[kWarps * 32]; } top;      // exact path: per-warp top-32 lists
+  struct { uint64_t s[32]; uint32_t id[32]; } ex;                         // phase 3: exact elements of the first 32 queue entries
 };
 constexpr uint32_t kSelQ = 1024;     // block-wide queue of top-n candidates (phase 3); more: exact scan
 
@@ -319,14 +339,23 @@ __device__ __forceinline__ void accumulate(const IndexView& ix, SmemLayout& S, c
       it = none; w = 0;
       if (g < G) { const uint32_t i = nl.gran_nbr[g]; w = nl.w[i]; it = __ldg(lists + (nl.goff[i] + g)); }
     };
+    // rounds of 32 granules are handed out by a block-wide counter: the warps finish within a round of each other
+    // whatever their luck with the probe sequences
+    auto grab = [&]() -> uint32_t {
+      uint32_t r = 0;
+      if (lane == 0) r = atomicAdd(&S.round, 1u);
+      return __shfl_sync(kFull, r, 0) * 32u;
+    };
     uint4 it; int32_t w;
-    fetch(warp * 32u + lane, it, w);
-    for (uint32_t base = warp * 32u; base < G; base += kThreads) {
+    uint32_t base = grab();
+    fetch(base + lane, it, w);
+    while (base < G) {
+      const uint32_t nbase = grab();
       uint4 nit; int32_t nw;                            // next round's granule travels while this one is inserted
-      fetch(base + kThreads + lane, nit, nw);
+      fetch(nbase + lane, nit, nw);
       insert_granule(S, it, w, last_idx, tab, mask, nclaim);
       if (guard && over_budget()) break;
-      it = nit; w = nw;
+      it = nit; w = nw; base = nbase;
     }
   } else {
     bool stop = false;
@@ -514,7 +543,9 @@ __device__ __forceinline__ uint32_t select_table(const IndexView& ix, const Pred
         const uint32_t t2_ = __reduce_max_sync(kFull, m); if (m == t2_) m = 0u;
         const uint32_t t3 = __reduce_max_sync(kFull, m);
         if (lane == 0) *reinterpret_cast<uint4*>(S.top4[warp]) = make_uint4(t0, t1, t2_, t3);
+        VMIS_CLK(S);
         __syncthreads();
+        VMIS_CLK(S);
         const uint32_t s32 = u32_sort_desc((lane >> 2) < kWarps ? S.top4[lane >> 2][lane & 3] : 0u, lane);
         const uint32_t bound = __shfl_sync(kFull, s32, (int)N - 1) >> kIdxBits;   // 0: fewer than N candidates so far
         thr = bound > 1u ? (bound - 1u) << kIdxBits : 1u;
@@ -527,49 +558,73 @@ __device__ __forceinline__ uint32_t select_table(const IndexView& ix, const Pred
         const int incl = warp_incl_scan(cnt, lane);
         uint32_t base = 0;
         if (lane == 31) base = atomicAdd(&S.qcount, (uint32_t)incl);
-        uint32_t pos = __shfl_sync(kFull, base, 31) + (uint32_t)(incl - cnt);
+        const uint32_t first = __shfl_sync(kFull, base, 31) + (uint32_t)(incl - cnt);
+        uint32_t pos = first;
 #pragma unroll
         for (int j = 0; j < 16; ++j) {
           if ((keep >> j) & 1u) { if (pos < kSelQ) queue[pos] = cc[j]; ++pos; }
         }
+        // the first 32 entries of the queue are rescored exactly right here, by the thread that queued them (all
+        // warps in parallel, off the serial tail): f64 g(idf) * A / (10 u), mod.rs:145-152
+        for (uint32_t p = first; p < pos && p < 32u; ++p) {
+          const Slot sl = tab[queue[p] & kIdxMask];
+          asm volatile("prefetch.global.L2 [%0];" ::"l"(ix.item_key + slot_key(sl)));   // read by the tail
+          const Elem e = exact_elem(ix, a, c, slot_key(sl), slot_val(sl), denom);
+          X.ex.s[p] = e.s; X.ex.id[p] = e.id;
+        }
       }
     }
+    VMIS_CLK(S);
     __syncthreads();
-    if (warp == 0) {
-      const uint32_t n = S.qcount;
-      bool ok = n <= kSelQ;
-      uint32_t best = 0;
-      if (ok) {
-        if (n <= 32u) {
-          best = (uint32_t)lane < n ? queue[lane] : 0u;
-        } else {
-          // cut to the 32 best coarse keys; the cut is proven if the last one is more than a unit below the N-th
-          for (uint32_t b = 0; b < n; b += 32u)
-            best = u32_merge_top(best, u32_sort_desc(b + lane < n ? queue[b + lane] : 0u, lane), lane);
-          ok = (__shfl_sync(kFull, best, 31) >> kIdxBits) + 1u < (__shfl_sync(kFull, best, (int)N - 1) >> kIdxBits);
-        }
+    VMIS_CLK(S);
+    const uint32_t n = S.qcount;
+    if (n <= 32u) {
+      // Rank by counting, all warps at once: the exact order is total (ids are unique), so the ranks are a
+      // permutation.  A group of 8 lanes owns one candidate (4 per warp), each lane compares it with 4 others, three
+      // shuffle steps add up the group — no serial tail, and every thread knows the outcome without a broadcast.
+      const uint32_t cnd = (uint32_t)warp * 4u + ((uint32_t)lane >> 3);
+      Elem my; my.s = 0; my.id = kEmpty;
+      if (cnd < n) { my.s = X.ex.s[cnd]; my.id = X.ex.id[cnd]; }
+      uint32_t rank = 0;
+#pragma unroll
+      for (uint32_t k = 0; k < 4u; ++k) {
+        const uint32_t j = ((uint32_t)lane & 7u) + 8u * k;
+        if (j < n) { Elem o; o.s = X.ex.s[j]; o.id = X.ex.id[j]; rank += better(o, my) ? 1u : 0u; }
       }
-      const uint32_t valid = __popc(__ballot_sync(kFull, best != 0));
-      const uint32_t take = min(valid, N);
+      rank += __shfl_xor_sync(kFull, rank, 1);
+      rank += __shfl_xor_sync(kFull, rank, 2);
+      rank += __shfl_xor_sync(kFull, rank, 4);
+      if (((uint32_t)lane & 7u) == 0u && cnd < n && rank < N) {
+        a.out_ids[(size_t)q * N + rank] = ix.item_key[my.id];
+        a.out_scores[(size_t)q * N + rank] = bits_score(my.s);
+      }
+      return min(n, N);
+    }
+    if (warp == 0) {
+      bool ok = n <= kSelQ;
+      uint32_t take = 0;
       if (ok) {
-        Elem x; x.s = 0; x.id = kEmpty;
-        if (best != 0) {
+        // cut to the 32 best coarse keys; the cut is proven if the last one is more than a unit below the N-th
+        uint32_t best = 0;
+        for (uint32_t b = 0; b < n; b += 32u)
+          best = u32_merge_top(best, u32_sort_desc(b + lane < n ? queue[b + lane] : 0u, lane), lane);
+        ok = (__shfl_sync(kFull, best, 31) >> kIdxBits) + 1u < (__shfl_sync(kFull, best, (int)N - 1) >> kIdxBits);
+        if (ok) {
+          take = N;
           const Slot sl = tab[best & kIdxMask];
-          // the external id is read after the sort: start pulling its line now
           asm volatile("prefetch.global.L2 [%0];" ::"l"(ix.item_key + slot_key(sl)));
-          x = exact_elem(ix, a, c, slot_key(sl), slot_val(sl), denom);
-        }
-        x = warp_sort_desc(x, lane);
-        if ((uint32_t)lane < take) {
-          a.out_ids[(size_t)q * N + lane] = ix.item_key[x.id];
-          a.out_scores[(size_t)q * N + lane] = bits_score(x.s);
+          Elem x = exact_elem(ix, a, c, slot_key(sl), slot_val(sl), denom);
+          x = warp_sort_desc(x, lane);
+          if ((uint32_t)lane < take) {
+            a.out_ids[(size_t)q * N + lane] = ix.item_key[x.id];
+            a.out_scores[(size_t)q * N + lane] = bits_score(x.s);
+          }
         }
       }
       if (lane == 0) { S.sel_ok = ok ? 1u : 0u; S.sel_count = take; }
     }
-    __syncthreads();
+    __syncthreads();     // sel_ok / sel_count are not rewritten before several later barriers: no trailing barrier
     const uint32_t ok = S.sel_ok, cnt = S.sel_count;
-    __syncthreads();
     if (ok) return cnt;
   }
   return select_exact<true, uint16_t>(ix, a, S, X, c, tab, nullptr, tab_cap);
@@ -624,13 +679,8 @@ vmis_predict_kernel(const IndexView ix, const PredictArgs a, const LaunchPlan pl
     if (q >= a.n_q) break;
     if (tid == 0) next_q = atomicAdd(ws.counter, 1u);
 
-#ifdef VMIS_PHASE_CLOCKS
-    long long clk[6]; int nclk = 0;
-#define VMIS_CLK() do { if (tid == 0 && nclk < 6) clk[nclk++] = clock64(); } while (0)
-#else
-#define VMIS_CLK() do {} while (0)
-#endif
-    VMIS_CLK();
+    if (tid == 0) VMIS_CLK_RESET(S);
+    VMIS_CLK(S);
     // ------------------------------------------------------------------ phase 0
     const uint32_t qo = a.q_off[q];
     const uint32_t Lfull = a.q_off[q + 1] - qo;
@@ -666,7 +716,7 @@ vmis_predict_kernel(const IndexView ix, const PredictArgs a, const LaunchPlan pl
     uint32_t nn = 0;                 // number of neighbours
     uint32_t postings_visited = 0;
 
-    VMIS_CLK();
+    VMIS_CLK(S);
     if (nd > 0 && K > 0 && M > 0 && (N > 0 || neighbors_mode)) {
       // ---------------------------------------------------------------- phase 1
       const uint2 ref0 = ix.post_ref[S.d_idx[0]];
@@ -860,7 +910,7 @@ vmis_predict_kernel(const IndexView ix, const PredictArgs a, const LaunchPlan pl
       continue;
     }
 
-    VMIS_CLK();
+    VMIS_CLK(S);
     // ------------------------------------------------------------------ phase 2a: neighbour directory
     {
       // all ones = empty; the capacity is a multiple of 4096: 16-byte stores
@@ -868,7 +918,7 @@ vmis_predict_kernel(const IndexView ix, const PredictArgs a, const LaunchPlan pl
       const uint32_t n4 = plan.tab_cap >> 1;
       for (uint32_t i = tid; i < n4; i += kThreads) t4[i] = make_uint4(kEmpty, kEmpty, kEmpty, kEmpty);
     }
-    if (tid == 0) { S.n_occ = 0; S.overflow = 0; }
+    if (tid == 0) { S.n_occ = 0; S.overflow = 0; S.round = 0; }
     // neighbours tid, tid + 256, ...: item list refs, weights, granule counts (the order of the neighbours is free)
     uint32_t my_g = 0, my_len = 0;
     for (uint32_t i = tid; i < nn; i += kThreads) {
@@ -911,7 +961,7 @@ vmis_predict_kernel(const IndexView ix, const PredictArgs a, const LaunchPlan pl
     }
     __syncthreads();
 
-    VMIS_CLK();
+    VMIS_CLK(S);
     // ------------------------------------------------------------------ phase 2b + 3
     QueryCtx c;
     c.q = q; c.u = u; c.last_idx = last_idx; c.cur_attr = cur_attr;
@@ -927,7 +977,7 @@ vmis_predict_kernel(const IndexView ix, const PredictArgs a, const LaunchPlan pl
       if (flat) accumulate<true>(ix, S, nl, nn, G, last_idx, stab, plan.tab_cap - 1, guard, plan.occ_cap);
       else accumulate<false>(ix, S, nl, nn, G, last_idx, stab, plan.tab_cap - 1, guard, plan.occ_cap);
       __syncthreads();
-      VMIS_CLK();
+      VMIS_CLK(S);
       if (!S.overflow && S.n_occ <= plan.occ_cap) {
         written = select_table(ix, a, S, X, reinterpret_cast<uint32_t*>(gran_nbr), c, stab, plan.tab_cap);
       } else {
@@ -935,7 +985,7 @@ vmis_predict_kernel(const IndexView ix, const PredictArgs a, const LaunchPlan pl
         Slot* gtab = ws.gtab + (size_t)blockIdx.x * ws.gtab_cap;
         uint32_t* gocc = ws.gtab_occ + (size_t)blockIdx.x * (ws.gtab_cap / 2);
         __syncthreads();
-        if (tid == 0) { S.n_occ = 0; S.overflow = 0; }
+        if (tid == 0) { S.n_occ = 0; S.overflow = 0; S.round = 0; }
         __syncthreads();
         if (flat) accumulate<true>(ix, S, nl, nn, G, last_idx, gtab, ws.gtab_cap - 1, false, 0u);
         else accumulate<false>(ix, S, nl, nn, G, last_idx, gtab, ws.gtab_cap - 1, false, 0u);
@@ -956,13 +1006,11 @@ vmis_predict_kernel(const IndexView ix, const PredictArgs a, const LaunchPlan pl
         vmis_query_stats_t st; st.postings_visited = postings_visited; st.n_neighbors = nn;
         st.neighbor_items = total_items; st.n_out = written;
 #ifdef VMIS_PHASE_CLOCKS
-        // tuning build: cycles of {phase 0, phases 1 + 1b, phase 2a, phase 2b} instead of the work counters
-        clk[nclk] = clock64();
-        if (nclk == 5) {
-          st.postings_visited = (uint32_t)(clk[1] - clk[0]); st.n_neighbors = (uint32_t)(clk[2] - clk[1]);
-          st.neighbor_items = (uint32_t)(clk[3] - clk[2]); st.n_out = (uint32_t)(clk[4] - clk[3]);
-          a.out_counts[q] = (uint32_t)(clk[5] - clk[4]);           // phase 3
-        }
+        // tuning build: the cycle counts between the probes replace the first ids of the row
+        VMIS_CLK(S);
+        for (uint32_t i = 0; i + 1 < S.nclk && i < N; ++i) a.out_ids[(size_t)q * N + i] = (uint64_t)(S.clk[i + 1] - S.clk[i]);
+        for (uint32_t i = S.nclk > 0 ? S.nclk - 1 : 0; i < N; ++i) a.out_ids[(size_t)q * N + i] = 0;
+        if (N > 11) a.out_ids[(size_t)q * N + 11] = S.qcount;
 #endif
         a.out_stats[q] = st;
       }

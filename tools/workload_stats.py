@@ -41,11 +41,11 @@ def run(qi, qo, reps=5):
                                       sc.data_ptr(), cnt.data_ptr(), None, sp)
     e1.record()
     torch.cuda.synchronize()
-    if os.environ.get("VMIS_CLOCKS"):     # tuning build -DVMIS_PHASE_CLOCKS: out_counts of the stats pass = phase-3 cycles
+    if os.environ.get("VMIS_CLOCKS"):     # tuning build -DVMIS_PHASE_CLOCKS: the stats pass leaves cycle counts in the ids
         lib.vmis_predict_batch_device(gix.handle, di.data_ptr(), do.data_ptr(), n, K, M, N, 0, ids.data_ptr(), sc.data_ptr(),
                                       cnt.data_ptr(), st.data_ptr(), sp)
         torch.cuda.synchronize()
-        return np.concatenate([st.cpu().numpy(), cnt.cpu().numpy()[:, None]], axis=1), e0.elapsed_time(e1) / reps
+        return ids.cpu().numpy()[:, :12], e0.elapsed_time(e1) / reps
     return st.cpu().numpy(), e0.elapsed_time(e1) / reps
 
 
@@ -54,7 +54,8 @@ L = np.diff(qo.astype(np.int64))
 print(f"all: {B} queries {ms:.3f} ms  {B / ms / 1e3:.2f} M qps")
 names = ["postings_visited", "n_neighbors", "neighbor_items", "n_out"]
 if os.environ.get("VMIS_CLOCKS"):
-    names = ["cycles phase 0", "cycles phase 1+1b", "cycles phase 2a", "cycles phase 2b", "cycles phase 3"]
+    names = ["cyc phase 0", "cyc phase 1+1b", "cyc phase 2a", "cyc 2b insert", "cyc 3 score+top4", "cyc 3 barrier", "cyc 3 sort+push",
+             "cyc 3 barrier", "cyc 3 tail+sync", "-", "-", "top-n queue entries"]
 for j, nm in enumerate(names):
     v = st[:, j]
     print(f"  {nm:18s} mean {v.mean():9.1f}  p50 {np.percentile(v, 50):8.0f}  p90 {np.percentile(v, 90):8.0f}  p99 {np.percentile(v, 99):8.0f}  max {v.max()}")
@@ -66,4 +67,4 @@ for l in range(1, 5):
     s2, ms2 = run(np.ascontiguousarray(items), off)
     print(f"L={l}: {len(sel)} queries {ms2:.3f} ms  {len(sel) / ms2 / 1e3:.2f} M qps  us/query/SM-slot {ms2 * 1e3 * 740 / len(sel):.1f}"
           f"  postings {s2[:, 0].mean():.0f} nn {s2[:, 1].mean():.0f} items {s2[:, 2].mean():.0f}"
-          + (f" n_out/phase2b {s2[:, 3].mean():.0f} phase3 {s2[:, 4].mean():.0f}" if s2.shape[1] > 4 else ""))
+          + (" | " + " ".join(f"{s2[:, j].mean():.0f}" for j in range(3, s2.shape[1])) if s2.shape[1] > 4 else ""))
