@@ -195,8 +195,10 @@ struct SmemLayout {
   uint32_t d_idx[kMaxSessionLen];    // distinct known items, most recent first
   uint8_t d_pos[kMaxSessionLen];
   ScanScratch scan;
-  uint32_t q;                        // current query
   uint32_t nd;
+  // the query this CTA runs next (double buffered): thread 0 publishes `q` while the current query is in phase 1;
+  // during phase 2b the last warp runs its phase 0 (short sessions) and leaves nd / u / L here with ok = 1
+  struct Next { uint32_t q, ok, nd, u, L; } nx[2];
   uint32_t n_occ;                    // occupied score-table slots of the current query
   uint32_t round;                    // phase 2b: next round of 32 granules to hand to a warp
   uint32_t overflow;                 // shared table over its occupancy budget → redo on the global table
@@ -282,21 +284,41 @@ __device__ __forceinline__ void insert_granule(SmemLayout& S, const uint4 it, in
   if (v1) o1 = atomicCAS(&tab[h1], kEmptySlot, make_slot(it.y, w));
   if (v2) o2 = atomicCAS(&tab[h2], kEmptySlot, make_slot(it.z, w));
   if (v3) o3 = atomicCAS(&tab[h3], kEmptySlot, make_slot(it.w, w));
-  // stage B: a claim is done, a hit adds to the low word (little endian: low word = A), the rest goes on probing
+  // a claim is done, a hit adds to the low word (little endian: low word = A), the rest goes on probing
   const uint32_t k0 = slot_key(o0), k1 = slot_key(o1), k2 = slot_key(o2), k3 = slot_key(o3);
   if (v0 && k0 == it.x) atomicAdd(reinterpret_cast<int*>(&tab[h0]), w);
   if (v1 && k1 == it.y) atomicAdd(reinterpret_cast<int*>(&tab[h1]), w);
   if (v2 && k2 == it.z) atomicAdd(reinterpret_cast<int*>(&tab[h2]), w);
   if (v3 && k3 == it.w) atomicAdd(reinterpret_cast<int*>(&tab[h3]), w);
   nclaim += (uint32_t)(v0 && k0 == kEmpty) + (uint32_t)(v1 && k1 == kEmpty) + (uint32_t)(v2 && k2 == kEmpty) + (uint32_t)(v3 && k3 == kEmpty);
-  uint32_t pend = (v0 && k0 != kEmpty && k0 != it.x ? 1u : 0u) | (v1 && k1 != kEmpty && k1 != it.y ? 2u : 0u) |
-                  (v2 && k2 != kEmpty && k2 != it.z ? 4u : 0u) | (v3 && k3 != kEmpty && k3 != it.w ? 8u : 0u);
+  const bool c0 = v0 && k0 != kEmpty && k0 != it.x, c1 = v1 && k1 != kEmpty && k1 != it.y;
+  const bool c2 = v2 && k2 != kEmpty && k2 != it.z, c3 = v3 && k3 != kEmpty && k3 != it.w;
+  uint32_t pend = 0;
+  if (__any_sync(kFull, c0 || c1 || c2 || c3)) {
+    // stage B: the second probes of the collided items, again all in flight before any result is looked at
+    const uint32_t g0 = (h0 + hash_stride(it.x)) & mask, g1 = (h1 + hash_stride(it.y)) & mask;
+    const uint32_t g2 = (h2 + hash_stride(it.z)) & mask, g3 = (h3 + hash_stride(it.w)) & mask;
+    Slot p0 = 0, p1 = 0, p2 = 0, p3 = 0;
+    if (c0) p0 = atomicCAS(&tab[g0], kEmptySlot, make_slot(it.x, w));
+    if (c1) p1 = atomicCAS(&tab[g1], kEmptySlot, make_slot(it.y, w));
+    if (c2) p2 = atomicCAS(&tab[g2], kEmptySlot, make_slot(it.z, w));
+    if (c3) p3 = atomicCAS(&tab[g3], kEmptySlot, make_slot(it.w, w));
+    const uint32_t q0 = slot_key(p0), q1 = slot_key(p1), q2 = slot_key(p2), q3 = slot_key(p3);
+    if (c0 && q0 == it.x) atomicAdd(reinterpret_cast<int*>(&tab[g0]), w);
+    if (c1 && q1 == it.y) atomicAdd(reinterpret_cast<int*>(&tab[g1]), w);
+    if (c2 && q2 == it.z) atomicAdd(reinterpret_cast<int*>(&tab[g2]), w);
+    if (c3 && q3 == it.w) atomicAdd(reinterpret_cast<int*>(&tab[g3]), w);
+    nclaim += (uint32_t)(c0 && q0 == kEmpty) + (uint32_t)(c1 && q1 == kEmpty) + (uint32_t)(c2 && q2 == kEmpty) + (uint32_t)(c3 && q3 == kEmpty);
+    pend = (c0 && q0 != kEmpty && q0 != it.x ? 1u : 0u) | (c1 && q1 != kEmpty && q1 != it.y ? 2u : 0u) |
+           (c2 && q2 != kEmpty && q2 != it.z ? 4u : 0u) | (c3 && q3 != kEmpty && q3 != it.w ? 8u : 0u);
+  }
+  // the few items that collided twice: one at a time, from the third probe position on
   while (__any_sync(kFull, pend != 0u)) {
     if (pend != 0u) {
       const uint32_t item = (pend & 1u) ? it.x : (pend & 2u) ? it.y : (pend & 4u) ? it.z : it.w;
       pend &= pend - 1u;
       const uint32_t stride = hash_stride(item);
-      uint32_t h = hash_slot(item);
+      uint32_t h = hash_slot(item) + stride;
       uint32_t tries = mask;                             // every other slot once
       for (;;) {
         h = (h + stride) & mask;
@@ -553,12 +575,8 @@ __device__ __forceinline__ uint32_t select_table(const IndexView& ix, const Pred
       uint32_t keep = 0;
 #pragma unroll
       for (int j = 0; j < 16; ++j) keep |= (cc[j] >= thr ? 1u : 0u) << j;
-      if (__any_sync(kFull, keep != 0u)) {
-        const int cnt = __popc(keep);
-        const int incl = warp_incl_scan(cnt, lane);
-        uint32_t base = 0;
-        if (lane == 31) base = atomicAdd(&S.qcount, (uint32_t)incl);
-        const uint32_t first = __shfl_sync(kFull, base, 31) + (uint32_t)(incl - cnt);
+      if (keep != 0u) {                                                   // a handful of lanes per query
+        const uint32_t first = atomicAdd(&S.qcount, (uint32_t)__popc(keep));
         uint32_t pos = first;
 #pragma unroll
         for (int j = 0; j < 16; ++j) {
@@ -631,6 +649,35 @@ __device__ __forceinline__ uint32_t select_table(const IndexView& ix, const Pred
 }
 
 
+// Phase 0 of the NEXT query, run by one warp while the others insert (phase 2b hands its rounds out dynamically, so
+// nobody waits for this warp): de-duplicate the evolving session (vmis_index.rs:335-348: a later duplicate of an item
+// does not count; unique items include unknown ones), translate ids through the HBM item hash, compact the distinct
+// known items in position order.  Sessions of more than 32 items are left to the block-wide path at the loop top.
+// d_idx / d_pos of the current query are dead after phase 2a, so the results go straight into them.
+__device__ __forceinline__ void phase0_next(const IndexView& ix, const PredictArgs& a, SmemLayout& S, SmemLayout::Next& nx) {
+  const uint32_t lane = threadIdx.x & 31u;
+  const uint32_t q = nx.q;
+  if (q >= a.n_q) return;
+  const uint32_t qo = a.q_off[q];
+  const uint32_t L = a.q_off[q + 1] - qo;
+  if (L > 32u) return;                                             // nx.ok stays 0
+  const uint32_t qb = qo - a.q_item_base;
+  const uint32_t valid = L == 32u ? kFull : (1u << L) - 1u;
+  // lane t holds the item at position t from the end; idle lanes get values that cannot match a valid lane's mask
+  const uint64_t it = lane < L ? a.q_items[qb + (L - 1u - lane)] : 0ull;
+  const uint32_t same = __match_any_sync(kFull, it) & valid;
+  const bool distinct = lane < L && (uint32_t)__ffs((int)same) - 1u == lane;   // the most recent occurrence counts
+  uint32_t my_idx = kEmpty;
+  if (distinct) my_idx = lookup_item(ix, it);
+  const uint32_t known = __ballot_sync(kFull, my_idx != kEmpty);
+  const uint32_t uniq = __ballot_sync(kFull, distinct);
+  if (my_idx != kEmpty) {
+    const uint32_t pos = (uint32_t)__popc(known & ((1u << lane) - 1u));
+    S.d_idx[pos] = my_idx; S.d_pos[pos] = (uint8_t)lane;
+  }
+  if (lane == 0) { nx.nd = (uint32_t)__popc(known); nx.u = (uint32_t)__popc(uniq); nx.L = L; nx.ok = 1u; }
+}
+
 __global__ void __launch_bounds__(kThreads, kCtasPerSm)
 vmis_predict_kernel(const IndexView ix, const PredictArgs a, const LaunchPlan plan, const Workspace ws) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -668,47 +715,54 @@ vmis_predict_kernel(const IndexView ix, const PredictArgs a, const LaunchPlan pl
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
 
-  // thread 0 always has the NEXT work item in flight: the global atomic's round trip overlaps the current query
+  // thread 0 always has the work item after the next in flight: the global atomic's round trip overlaps a query
   uint32_t next_q = 0;
-  if (tid == 0) next_q = atomicAdd(ws.counter, 1u);
-  for (;;) {
-    __syncthreads();
-    if (tid == 0) S.q = next_q;
-    __syncthreads();
-    const uint32_t q = S.q;
+  uint32_t nb = 0;                                                 // S.nx[nb]: the query to run now
+  if (tid == 0) {
+    S.nx[0].q = atomicAdd(ws.counter, 1u); S.nx[0].ok = 0u;
+    next_q = atomicAdd(ws.counter, 1u);
+  }
+  for (;; nb ^= 1u) {
+    __syncthreads();                                               // the previous query is finished; S.nx[nb] is complete
+    const uint32_t q = S.nx[nb].q;
     if (q >= a.n_q) break;
-    if (tid == 0) next_q = atomicAdd(ws.counter, 1u);
+    if (tid == 0) { S.nx[nb ^ 1u].q = next_q; S.nx[nb ^ 1u].ok = 0u; next_q = atomicAdd(ws.counter, 1u); }
 
     if (tid == 0) VMIS_CLK_RESET(S);
     VMIS_CLK(S);
     // ------------------------------------------------------------------ phase 0
-    const uint32_t qo = a.q_off[q];
-    const uint32_t Lfull = a.q_off[q + 1] - qo;
-    const uint32_t qb = qo - a.q_item_base;
-    const uint32_t L = Lfull > (uint32_t)kMaxSessionLen ? 0u : Lfull;   // over-long sessions are rejected host-side
-    if (tid < (int)L) q_item[tid] = a.q_items[qb + (L - 1 - tid)];
-    __syncthreads();
-    uint32_t my_idx = kEmpty;
-    bool distinct = false;
-    if (tid < (int)L) {
-      const uint64_t it = q_item[tid];
-      distinct = true;
-      for (int t = 0; t < tid; ++t) if (q_item[t] == it) { distinct = false; break; }
-      if (distinct) my_idx = lookup_item(ix, it);
+    uint32_t nd, u, L;
+    if (S.nx[nb].ok) {
+      // done by the last warp during the previous query's phase 2b (phase0_next)
+      nd = S.nx[nb].nd; u = S.nx[nb].u; L = S.nx[nb].L;
+    } else {
+      const uint32_t qo = a.q_off[q];
+      const uint32_t Lfull = a.q_off[q + 1] - qo;
+      const uint32_t qb = qo - a.q_item_base;
+      L = Lfull > (uint32_t)kMaxSessionLen ? 0u : Lfull;             // over-long sessions are rejected host-side
+      if (tid < (int)L) q_item[tid] = a.q_items[qb + (L - 1 - tid)];
+      __syncthreads();
+      uint32_t my_idx = kEmpty;
+      bool distinct = false;
+      if (tid < (int)L) {
+        const uint64_t it = q_item[tid];
+        distinct = true;
+        for (int t = 0; t < tid; ++t) if (q_item[t] == it) { distinct = false; break; }
+        if (distinct) my_idx = lookup_item(ix, it);
+      }
+      // one packed scan: low half compacts the distinct KNOWN items in position order, high half counts the
+      // unique items including unknown ones (vmis_index.rs:335-339)
+      {
+        const int flag = (my_idx != kEmpty) ? 1 : 0;
+        int total;
+        const int pos = block_excl_scan(flag | ((distinct ? 1 : 0) << 16), S.scan, par, total) & 0xFFFF;
+        if (flag) { S.d_idx[pos] = my_idx; S.d_pos[pos] = (uint8_t)tid; }
+        if (tid == 0) S.nd = (uint32_t)total & 0xFFFFu;
+        u = (uint32_t)total >> 16;
+      }
+      __syncthreads();
+      nd = S.nd;
     }
-    // one packed scan: low half compacts the distinct KNOWN items in position order, high half counts the
-    // unique items including unknown ones (vmis_index.rs:335-339)
-    uint32_t u;
-    {
-      const int flag = (my_idx != kEmpty) ? 1 : 0;
-      int total;
-      const int pos = block_excl_scan(flag | ((distinct ? 1 : 0) << 16), S.scan, par, total) & 0xFFFF;
-      if (flag) { S.d_idx[pos] = my_idx; S.d_pos[pos] = (uint8_t)tid; }
-      if (tid == 0) S.nd = (uint32_t)total & 0xFFFFu;
-      u = (uint32_t)total >> 16;
-    }
-    __syncthreads();
-    const uint32_t nd = S.nd;
     // most recent item: removed from the result (mod.rs:157-160); attributes for the adult rule (:186)
     const uint32_t last_idx = (nd > 0 && S.d_pos[0] == 0) ? S.d_idx[0] : kEmpty;
     const uint32_t cur_attr = (a.biz && last_idx != kEmpty) ? ix.attr[last_idx] : 0u;
@@ -974,6 +1028,8 @@ vmis_predict_kernel(const IndexView ix, const PredictArgs a, const LaunchPlan pl
       written = 0;
     } else {
       const bool guard = total_items > plan.occ_cap;                // the neighbours may hold more distinct items than the budget
+      // d_idx / d_pos of this query are dead from here on: the last warp prepares the next query before it joins in
+      if (warp == kWarps - 1) phase0_next(ix, a, S, S.nx[nb ^ 1u]);
       if (flat) accumulate<true>(ix, S, nl, nn, G, last_idx, stab, plan.tab_cap - 1, guard, plan.occ_cap);
       else accumulate<false>(ix, S, nl, nn, G, last_idx, stab, plan.tab_cap - 1, guard, plan.occ_cap);
       __syncthreads();
