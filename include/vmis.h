@@ -35,6 +35,13 @@ extern "C" {
 #define VMIS_ERR_CUDA (-3)     /* CUDA runtime error or no usable device        */
 #define VMIS_ERR_LIMIT (-4)    /* k / m / session length beyond kernel limits   */
 
+/* Longest evolving session a query may carry (the reference's HPO grid stops at 100 items,
+ * hyperparameter_search.rs:20; the session weight of mod.rs:110-116 is zero from position 100 on). */
+#define VMIS_MAX_SESSION_LEN 128
+/* vmis_predict_batch_device cannot fail a launch that is already queued: a query whose evolving session exceeds
+ * VMIS_MAX_SESSION_LEN gets this value in out_counts (and no recommendations) instead of a count. */
+#define VMIS_COUNT_TOO_LONG 0xFFFFFFFFu
+
 /* device ordinal for a host-only handle: the index is built and the trait accessors work, but every
  * query entry point fails with VMIS_ERR_CUDA (used by CPU-side tests of the builders). */
 #define VMIS_DEVICE_NONE (-1)
@@ -181,7 +188,9 @@ int vmis_predict_batch(const vmis_index_t* index, const uint64_t* q_items, const
                        uint64_t* out_ids, double* out_scores, uint32_t* out_counts, void* stream);
 
 /* Same computation with every buffer already resident on the index's device (no copies, no sync;
- * work is enqueued on `stream`; NULL = the CUDA default stream).  out_stats may be NULL. */
+ * work is enqueued on `stream`; NULL = the CUDA default stream).  out_stats may be NULL.  The query lengths are on
+ * the device, so the host cannot reject an over-long evolving session here: such a query comes back with
+ * out_counts[q] == VMIS_COUNT_TOO_LONG and an empty row (vmis_predict_batch returns VMIS_ERR_LIMIT instead). */
 int vmis_predict_batch_device(const vmis_index_t* index, const uint64_t* d_q_items, const uint32_t* d_q_off,
                               uint32_t n_q, uint32_t k, uint32_t m, uint32_t how_many, int enable_business_logic,
                               uint64_t* d_out_ids, double* d_out_scores, uint32_t* d_out_counts,
@@ -246,6 +255,13 @@ int vmis_batcher_predict(vmis_batcher_t* batcher, const uint64_t* evolving_sessi
                          double* out_scores);
 int vmis_batcher_stats(vmis_batcher_t* batcher, uint64_t* n_batches, uint64_t* n_requests);
 void vmis_batcher_destroy(vmis_batcher_t* batcher);
+/* Open-loop load generator over the batcher (measurement aid for the online call shape): n_threads caller threads
+ * replay the evolving sessions of a CSR batch at target_rps for duration_ms; request j is due at t0 + j/target_rps
+ * and its latency (microseconds, into lat_us[0..cap)) counts from that due time.  Returns the number of completed
+ * requests or a negative VMIS_ERR_*. */
+long long vmis_batcher_load_test(vmis_batcher_t* batcher, const uint64_t* q_items, const uint32_t* q_off, uint32_t n_q,
+                                 uint32_t n_threads, double target_rps, uint32_t duration_ms, float* lat_us, size_t cap,
+                                 double* achieved_rps);
 
 /* ---- misc ---------------------------------------------------------------- */
 

@@ -31,6 +31,9 @@ int fail(int code, const char* fmt, ...) {
   g_err_code = code;
   return code;
 }
+// every successful public call that can fail clears the code, so `vmis_last_error_code() != 0` means "the last call
+// on this thread failed" (the code used to stick)
+inline int ok() { g_err_code = 0; return VMIS_OK; }
 #define CU_TRY(expr)                                                                     \
   do {                                                                                   \
     cudaError_t e__ = (expr);                                                            \
@@ -55,6 +58,13 @@ struct CallCtx {
 };
 
 }  // namespace
+
+namespace vmis {
+void set_last_error(int code, const char* msg) {
+  if (code == VMIS_OK) { g_err.clear(); g_err_code = 0; }
+  else fail(code, "%s", msg ? msg : "");
+}
+}  // namespace vmis
 
 struct vmis_index {
   int device = 0;
@@ -432,6 +442,7 @@ const char* vmis_version(void) { return "serenade_b200 0.1 (sm_100a)"; }
 
 vmis_index_t* vmis_index_from_sessions(const uint64_t* items, const uint64_t* sess_off, const uint32_t* sess_ts,
                                        size_t n_sessions, size_t m, size_t max_len, double idf_weighting, int device) {
+  g_err_code = 0;
   if (!sess_off || !sess_ts || (!items && n_sessions && sess_off[n_sessions] > 0)) { fail(VMIS_ERR_ARG, "NULL session arrays"); return nullptr; }
   std::unique_ptr<vmis_index> ix(new vmis_index());
   ix->sessions.off.assign(sess_off, sess_off + n_sessions + 1);
@@ -443,6 +454,7 @@ vmis_index_t* vmis_index_from_sessions(const uint64_t* items, const uint64_t* se
 vmis_index_t* vmis_index_from_sessions_sharded(const uint64_t* items, const uint64_t* sess_off, const uint32_t* sess_ts,
                                                size_t n_sessions, size_t m, size_t max_len, double idf_weighting,
                                                int device, uint32_t shard, uint32_t n_shards) {
+  g_err_code = 0;
   if (!sess_off || !sess_ts || (!items && n_sessions && sess_off[n_sessions] > 0)) { fail(VMIS_ERR_ARG, "NULL session arrays"); return nullptr; }
   std::unique_ptr<vmis_index> ix(new vmis_index());
   ix->sessions.off.assign(sess_off, sess_off + n_sessions + 1);
@@ -454,6 +466,7 @@ vmis_index_t* vmis_index_from_sessions_sharded(const uint64_t* items, const uint
 vmis_index_t* vmis_index_from_device_sessions(const uint64_t* d_items, const uint64_t* d_sess_off, const uint32_t* d_sess_ts,
                                               size_t n_sessions, size_t m, size_t max_len, double idf_weighting, int device,
                                               uint32_t shard, uint32_t n_shards) {
+  g_err_code = 0;
   if (!d_items || !d_sess_off || !d_sess_ts) { fail(VMIS_ERR_ARG, "NULL device session arrays"); return nullptr; }
   if (max_len == 0) { fail(VMIS_ERR_ARG, "the device build needs an explicit max_len"); return nullptr; }
   std::unique_ptr<vmis_index> ix(new vmis_index());
@@ -466,6 +479,7 @@ vmis_index_t* vmis_index_from_device_sessions(const uint64_t* d_items, const uin
 
 vmis_index_t* vmis_index_synth(uint64_t seed, uint64_t n_items, uint64_t n_sessions, size_t m, size_t max_len,
                                double idf_weighting, int device, uint32_t shard, uint32_t n_shards) {
+  g_err_code = 0;
   if (max_len == 0) max_len = 34;
   std::unique_ptr<vmis_index> ix(new vmis_index());
   if (select_device(device, &ix->sm_count) != VMIS_OK) return nullptr;
@@ -492,6 +506,7 @@ static vmis_index_t* finish_prebuilt(std::unique_ptr<vmis_index> ix, vmis::Prebu
 }
 
 vmis_index_t* vmis_index_from_avro_sharded(const char* base_path, int device, uint32_t shard, uint32_t n_shards) {
+  g_err_code = 0;
   if (!base_path) { fail(VMIS_ERR_ARG, "path is NULL"); return nullptr; }
   std::unique_ptr<vmis_index> ix(new vmis_index());
   vmis::PrebuiltIndex P; vmis::AvroLoadInfo li; std::string err;
@@ -507,6 +522,7 @@ vmis_index_t* vmis_index_from_parts(const uint64_t* item_ids, const uint64_t* po
                                     const double* idf, const uint8_t* attr_or_null, size_t n_items, const uint64_t* items,
                                     const uint64_t* sess_off, const uint32_t* sess_ts, size_t n_sessions, int device,
                                     uint32_t shard, uint32_t n_shards) {
+  g_err_code = 0;
   if (!item_ids || !post_off || !idf || !sess_off || !sess_ts || (!post_sessions && n_items && post_off[n_items] > 0) ||
       (!items && n_sessions && sess_off[n_sessions] > 0)) { fail(VMIS_ERR_ARG, "NULL index arrays"); return nullptr; }
   std::unique_ptr<vmis_index> ix(new vmis_index());
@@ -524,6 +540,7 @@ vmis_index_t* vmis_index_from_parts(const uint64_t* item_ids, const uint64_t* po
 }
 
 int vmis_index_prebuilt_info(const vmis_index_t* ix, vmis_prebuilt_info_t* out) {
+  g_err_code = 0;
   if (!ix || !out) return fail(VMIS_ERR_ARG, "NULL argument");
   *out = ix->prebuilt;
   if (!ix->prebuilt.prebuilt) out->m_carry = ix->flat.m_carry;
@@ -533,6 +550,7 @@ int vmis_index_prebuilt_info(const vmis_index_t* ix, vmis_prebuilt_info_t* out) 
 // The index in the production on-disk format (the reference computes it offline with Spark; vmis_index.rs:85-313 reads
 // it back): posting lists as reference session indices, idf, attributes, and the host mirror of the sessions.
 int vmis_index_to_avro(const vmis_index_t* ix, const char* base_path, const char* codec, uint32_t n_files) {
+  g_err_code = 0;
   if (!ix || !base_path) return fail(VMIS_ERR_ARG, "NULL argument");
   if (ix->sessions.size() == 0) return fail(VMIS_ERR_ARG, "this handle has no host mirror of the sessions (blob-loaded or device-generated)");
   if (ix->flat.n_shards != 1) return fail(VMIS_ERR_ARG, "export an unsharded handle");
@@ -566,6 +584,7 @@ int vmis_index_to_avro(const vmis_index_t* ix, const char* base_path, const char
 // ---- serialised index blob: the "checkpoint" of this path (the reference rebuilds or re-reads Avro at start-up,
 // serving.rs:37-52; loading the flat arrays is a plain read + upload) ----
 int vmis_index_save(const vmis_index_t* ix, const char* path) {
+  g_err_code = 0;
   if (!ix || !path) return fail(VMIS_ERR_ARG, "NULL argument");
   if (ix->device == VMIS_DEVICE_NONE) return fail(VMIS_ERR_ARG, "only device-resident indexes can be saved");
   CU_TRY(cudaSetDevice(ix->device));
@@ -589,6 +608,7 @@ int vmis_index_save(const vmis_index_t* ix, const char* path) {
 }
 
 vmis_index_t* vmis_index_load(const char* path, int device) {
+  g_err_code = 0;
   if (!path) { fail(VMIS_ERR_ARG, "path is NULL"); return nullptr; }
   FILE* f = std::fopen(path, "rb");
   if (!f) { fail(VMIS_ERR_IO, "cannot open %s", path); return nullptr; }
@@ -628,6 +648,7 @@ vmis_index_t* vmis_index_load(const char* path, int device) {
 }
 
 int vmis_index_export_shard(const vmis_index_t* ix, void* handle64) {
+  g_err_code = 0;
   if (!ix || !handle64 || ix->device == VMIS_DEVICE_NONE) return fail(VMIS_ERR_ARG, "no device shard to export");
   static_assert(sizeof(cudaIpcMemHandle_t) == 64, "IPC handle size");
   CU_TRY(cudaSetDevice(ix->device));
@@ -638,6 +659,7 @@ int vmis_index_export_shard(const vmis_index_t* ix, void* handle64) {
 }
 
 int vmis_index_attach_shard(vmis_index_t* ix, uint32_t shard, const void* handle64) {
+  g_err_code = 0;
   if (!ix || !handle64 || ix->device == VMIS_DEVICE_NONE) return fail(VMIS_ERR_ARG, "NULL argument");
   if (shard >= ix->view.n_shards || shard == ix->shard) return fail(VMIS_ERR_ARG, "cannot attach shard %u", shard);
   CU_TRY(cudaSetDevice(ix->device));
@@ -651,6 +673,7 @@ int vmis_index_attach_shard(vmis_index_t* ix, uint32_t shard, const void* handle
 }
 
 int vmis_index_attach_shard_ptr(vmis_index_t* ix, uint32_t shard, const void* device_ptr) {
+  g_err_code = 0;
   if (!ix || !device_ptr || ix->device == VMIS_DEVICE_NONE) return fail(VMIS_ERR_ARG, "NULL argument");
   if (shard >= ix->view.n_shards || shard == ix->shard) return fail(VMIS_ERR_ARG, "cannot attach shard %u", shard);
   ix->view.post_shard[shard] = static_cast<const uint32_t*>(device_ptr);
@@ -667,6 +690,7 @@ const void* vmis_index_shard_ptr(const vmis_index_t* ix) {
 struct vmis_sessions { vmis::Sessions s; };
 
 vmis_sessions_t* vmis_sessions_from_csv(const char* path) {
+  g_err_code = 0;
   if (!path) { fail(VMIS_ERR_ARG, "path is NULL"); return nullptr; }
   std::unique_ptr<vmis_sessions> h(new vmis_sessions());
   std::string err;
@@ -676,6 +700,7 @@ vmis_sessions_t* vmis_sessions_from_csv(const char* path) {
 
 int vmis_sessions_view(const vmis_sessions_t* h, const uint64_t** items, const uint64_t** sess_off, const uint32_t** sess_ts,
                        size_t* n_sessions) {
+  g_err_code = 0;
   if (!h || !items || !sess_off || !sess_ts || !n_sessions) return fail(VMIS_ERR_ARG, "NULL argument");
   *items = h->s.items.data(); *sess_off = h->s.off.data(); *sess_ts = h->s.ts.data(); *n_sessions = h->s.size();
   return VMIS_OK;
@@ -684,6 +709,7 @@ int vmis_sessions_view(const vmis_sessions_t* h, const uint64_t** items, const u
 void vmis_sessions_free(vmis_sessions_t* h) { delete h; }
 
 vmis_index_t* vmis_index_from_csv_ex(const char* path, size_t m, double idf_weighting, size_t max_len, int device) {
+  g_err_code = 0;
   if (!path) { fail(VMIS_ERR_ARG, "path is NULL"); return nullptr; }
   std::unique_ptr<vmis_index> ix(new vmis_index());
   std::string err;
@@ -692,10 +718,12 @@ vmis_index_t* vmis_index_from_csv_ex(const char* path, size_t m, double idf_weig
 }
 
 vmis_index_t* vmis_index_from_csv(const char* path, size_t m, double idf_weighting, int device) {
+  g_err_code = 0;
   return vmis_index_from_csv_ex(path, m, idf_weighting, 0, device);
 }
 
 int vmis_index_set_attributes(vmis_index_t* ix, const uint64_t* items, const uint8_t* flags, size_t n) {
+  g_err_code = 0;
   if (!ix || (n && (!items || !flags))) return fail(VMIS_ERR_ARG, "NULL argument");
   for (size_t i = 0; i < n; ++i) {
     const uint32_t d = vmis::host_lookup_item(ix->flat, items[i]);
@@ -721,6 +749,7 @@ void vmis_index_free(vmis_index_t* ix) {
 }
 
 int vmis_index_stats(const vmis_index_t* ix, vmis_stats_t* out) {
+  g_err_code = 0;
   if (!ix || !out) return fail(VMIS_ERR_ARG, "NULL argument");
   out->n_sessions = ix->sessions.size() ? ix->sessions.size() : ix->n_sessions_kept;
   out->n_sessions_kept = ix->n_sessions_kept;
@@ -737,12 +766,14 @@ int vmis_index_stats(const vmis_index_t* ix, vmis_stats_t* out) {
 int vmis_predict_batch(const vmis_index_t* ix, const uint64_t* q_items, const uint32_t* q_off, uint32_t n_q, uint32_t k,
                        uint32_t m, uint32_t how_many, int biz, uint64_t* out_ids, double* out_scores,
                        uint32_t* out_counts, void* stream) {
+  g_err_code = 0;
   return host_batch(ix, q_items, q_off, n_q, k, m, how_many, biz, out_ids, out_scores, out_counts, nullptr, nullptr, stream);
 }
 
 int vmis_find_neighbors_batch(const vmis_index_t* ix, const uint64_t* q_items, const uint32_t* q_off, uint32_t n_q,
                               uint32_t k, uint32_t m, uint32_t* out_sess, double* out_sim, uint32_t* out_counts,
                               void* stream) {
+  g_err_code = 0;
   if (!out_sess || !out_sim) return fail(VMIS_ERR_ARG, "NULL output buffer");
   return host_batch(ix, q_items, q_off, n_q, k, m, 0, 0, nullptr, nullptr, out_counts, out_sess, out_sim, stream);
 }
@@ -750,6 +781,7 @@ int vmis_find_neighbors_batch(const vmis_index_t* ix, const uint64_t* q_items, c
 int vmis_predict_batch_device(const vmis_index_t* cix, const uint64_t* d_q_items, const uint32_t* d_q_off, uint32_t n_q,
                               uint32_t k, uint32_t m, uint32_t how_many, int biz, uint64_t* d_out_ids,
                               double* d_out_scores, uint32_t* d_out_counts, vmis_query_stats_t* d_out_stats, void* stream_) {
+  g_err_code = 0;
   vmis_index* ix = const_cast<vmis_index*>(cix);
   vmis::LaunchPlan plan;
   int rc = check_common(ix, k, m, &plan);
@@ -772,6 +804,7 @@ int vmis_predict_batch_device(const vmis_index_t* cix, const uint64_t* d_q_items
 
 int vmis_predict(const vmis_index_t* ix, const uint64_t* ev, size_t len, size_t k, size_t m, size_t how_many, int biz,
                  uint64_t* out_ids, double* out_scores) {
+  g_err_code = 0;
   if (len > 0xFFFFFFFFull || k > 0xFFFFFFFFull || m > 0xFFFFFFFFull || how_many > 0xFFFFFFFFull)
     return fail(VMIS_ERR_ARG, "argument out of range");
   const uint32_t off[2] = {0u, (uint32_t)len};
@@ -782,12 +815,14 @@ int vmis_predict(const vmis_index_t* ix, const uint64_t* ev, size_t len, size_t 
 }
 
 const uint64_t* vmis_items_for_session(const vmis_index_t* ix, uint32_t session, size_t* len) {
+  g_err_code = 0;
   if (!ix || session >= ix->sessions.size()) { fail(VMIS_ERR_ARG, "session %u out of range", session); if (len) *len = 0; return nullptr; }
   if (len) *len = ix->sessions.off[session + 1] - ix->sessions.off[session];
   return ix->sessions.items.data() + ix->sessions.off[session];
 }
 
 int vmis_idf(const vmis_index_t* ix, uint64_t item, double* out) {
+  g_err_code = 0;
   if (!ix || !out) return fail(VMIS_ERR_ARG, "NULL argument");
   const uint32_t d = vmis::host_lookup_item(ix->flat, item);
   if (d == vmis::kEmpty) return fail(VMIS_ERR_ARG, "unknown item %llu", (unsigned long long)item);
@@ -796,6 +831,7 @@ int vmis_idf(const vmis_index_t* ix, uint64_t item, double* out) {
 }
 
 int vmis_find_attributes(const vmis_index_t* ix, uint64_t item) {
+  g_err_code = 0;
   if (!ix) return 0;
   const uint32_t d = vmis::host_lookup_item(ix->flat, item);
   if (d == vmis::kEmpty) return 0;
@@ -804,6 +840,7 @@ int vmis_find_attributes(const vmis_index_t* ix, uint64_t item) {
 }
 
 size_t vmis_postings(const vmis_index_t* ix, uint64_t item, uint32_t* out, size_t cap) {
+  g_err_code = 0;
   if (!ix) return 0;
   const uint32_t d = vmis::host_lookup_item(ix->flat, item);
   if (d == vmis::kEmpty) return 0;
@@ -816,6 +853,7 @@ size_t vmis_postings(const vmis_index_t* ix, uint64_t item, uint32_t* out, size_
 }
 
 int vmis_session_timestamp(const vmis_index_t* ix, uint32_t session, uint32_t* out) {
+  g_err_code = 0;
   if (!ix || !out || session >= ix->sessions.size()) return fail(VMIS_ERR_ARG, "session %u out of range", session);
   *out = ix->sessions.ts[session];
   return VMIS_OK;

@@ -732,6 +732,7 @@ vmis_predict_kernel(const IndexView ix, const PredictArgs a, const LaunchPlan pl
     VMIS_CLK(S);
     // ------------------------------------------------------------------ phase 0
     uint32_t nd, u, L;
+    bool too_long = false;
     if (S.nx[nb].ok) {
       // done by the last warp during the previous query's phase 2b (phase0_next)
       nd = S.nx[nb].nd; u = S.nx[nb].u; L = S.nx[nb].L;
@@ -739,7 +740,8 @@ vmis_predict_kernel(const IndexView ix, const PredictArgs a, const LaunchPlan pl
       const uint32_t qo = a.q_off[q];
       const uint32_t Lfull = a.q_off[q + 1] - qo;
       const uint32_t qb = qo - a.q_item_base;
-      L = Lfull > (uint32_t)kMaxSessionLen ? 0u : Lfull;             // over-long sessions are rejected host-side
+      too_long = Lfull > (uint32_t)kMaxSessionLen;                   // rejected up front by the host API; flagged per query here
+      L = too_long ? 0u : Lfull;
       if (tid < (int)L) q_item[tid] = a.q_items[qb + (L - 1 - tid)];
       __syncthreads();
       uint32_t my_idx = kEmpty;
@@ -1057,7 +1059,7 @@ vmis_predict_kernel(const IndexView ix, const PredictArgs a, const LaunchPlan pl
       a.out_ids[(size_t)q * N + i] = 0; a.out_scores[(size_t)q * N + i] = 0.0;
     }
     if (tid == 0) {
-      a.out_counts[q] = written;
+      a.out_counts[q] = too_long ? VMIS_COUNT_TOO_LONG : written;
       if (a.out_stats) {
         vmis_query_stats_t st; st.postings_visited = postings_visited; st.n_neighbors = nn;
         st.neighbor_items = total_items; st.n_out = written;

@@ -19,7 +19,7 @@ constexpr uint32_t kEmpty = 0xFFFFFFFFu;
 constexpr int kThreads = VMIS_THREADS;   // one CTA per evolving session
 constexpr int kCtasPerSm = VMIS_CTAS;    // resident CTAs per SM the kernel is compiled (register-bounded) for
 constexpr int kWarps = kThreads / 32;
-constexpr int kMaxSessionLen = 128;      // evolving-session length limit of the kernel (reference HPO grid: <= 100)
+constexpr int kMaxSessionLen = VMIS_MAX_SESSION_LEN;   // evolving-session length limit of the kernel (reference HPO grid: <= 100)
 constexpr uint32_t kMaxK = 2048;         // keeps the int32 item numerators exact
 constexpr uint32_t kMaxM = 8192;         // shared-memory bound of the m-sample buffers
 constexpr int kMaxShards = 8;            // item-sharded postings: one shard per GPU of a box

@@ -52,6 +52,9 @@ size_t session_length_p99_5(const Sessions& s);
 bool build_flat_index(const Sessions& s, size_t m, size_t max_len, double idf_weighting, uint32_t n_shards,
                       FlatIndex* out, std::string* err);
 
+// vmis_last_error() / vmis_last_error_code() of the calling thread (capi.cu); code VMIS_OK clears them
+void set_last_error(int code, const char* msg);
+
 // dense index of an external item id, kEmpty if unknown
 uint32_t host_lookup_item(const FlatIndex& f, uint64_t item);
 

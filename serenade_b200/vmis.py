@@ -91,6 +91,7 @@ def load_library():
         "vmis_batcher_predict": (i32, [vp, _u64p, sz, _u64p, _f64p]),
         "vmis_batcher_stats": (i32, [vp, _u64p, _u64p]),
         "vmis_batcher_destroy": (None, [vp]),
+        "vmis_batcher_load_test": (C.c_longlong, [vp, _u64p, _u32p, u32, u32, f64, u32, C.POINTER(C.c_float), sz, _f64p]),
         "vmis_server_create": (vp, [vp, u32, u32, u32, u32, i32, u32, u32, u64, u64]),
         "vmis_server_recommend": (i32, [vp, C.c_char_p, u64, i32, _u64p, _f64p]),
         "vmis_server_session_window": (i32, [vp, C.c_char_p, u64, i32, _u64p, sz]),
@@ -120,7 +121,7 @@ EXPORTED_SYMBOLS = ("vmis_index_from_csv", "vmis_index_from_csv_ex", "vmis_sessi
                     "vmis_predict_batch_device", "vmis_predict", "vmis_find_neighbors_batch", "vmis_items_for_session",
                     "vmis_idf", "vmis_find_attributes", "vmis_postings", "vmis_session_timestamp",
                     "vmis_synth_sessions", "vmis_synth_queries", "vmis_batcher_create", "vmis_batcher_predict",
-                    "vmis_batcher_stats", "vmis_batcher_destroy", "vmis_server_create", "vmis_server_recommend",
+                    "vmis_batcher_stats", "vmis_batcher_destroy", "vmis_batcher_load_test", "vmis_server_create", "vmis_server_recommend",
                     "vmis_server_session_window", "vmis_server_stored_items", "vmis_server_set_clock", "vmis_server_stats",
                     "vmis_server_destroy", "vmis_md5", "vmis_last_error", "vmis_last_error_code",
                     "vmis_version")
@@ -431,6 +432,20 @@ class Batcher:
         a, b = C.c_uint64(), C.c_uint64()
         _check(load_library().vmis_batcher_stats(self._b, C.byref(a), C.byref(b)))
         return {"batches": a.value, "requests": b.value}
+
+    def load_test(self, sessions, target_rps, duration_ms=1000, n_threads=64):
+        """open-loop replay of the evolving sessions (CSR pair) at target_rps → (latencies in us, achieved rps)"""
+        q_items, q_off = sessions
+        q_items = np.ascontiguousarray(q_items, dtype=np.uint64)
+        q_off = np.ascontiguousarray(q_off, dtype=np.uint32)
+        cap = int(target_rps * duration_ms / 1e3) + 1
+        lat = np.zeros(cap, dtype=np.float32)
+        rps = C.c_double()
+        n = load_library().vmis_batcher_load_test(self._b, _p(q_items, C.c_uint64), _p(q_off, C.c_uint32), len(q_off) - 1,
+                                                  n_threads, float(target_rps), int(duration_ms),
+                                                  _p(lat, C.c_float), cap, C.byref(rps))
+        _check(int(n) if n < 0 else 0)
+        return lat[:min(int(n), cap)], rps.value
 
     def close(self):
         if getattr(self, "_b", None) and _lib is not None:
