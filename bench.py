@@ -185,18 +185,22 @@ def bind_to_gpu_numa(local_rank):
 
 
 class NvlinkCounters:
-    """NVML NVLink data counters of one GPU (KiB, summed over links); None when the driver does not expose them."""
+    """NVML NVLink data counters of one GPU (bytes, all links); `why` says what failed when the driver hides them."""
 
-    def __init__(self, gpu_index):
-        self.h = None
+    def __init__(self, cuda_index):
+        self.h, self.why = None, None
         try:
             import pynvml
+            import torch
             pynvml.nvmlInit()
-            self.nv, self.h = pynvml, pynvml.nvmlDeviceGetHandleByIndex(gpu_index)
-            self.fields = [getattr(pynvml, "NVML_FI_DEV_NVLINK_THROUGHPUT_DATA_RX"),
-                           getattr(pynvml, "NVML_FI_DEV_NVLINK_THROUGHPUT_DATA_TX")]
-        except Exception:  # noqa: BLE001
-            self.h = None
+            p = torch.cuda.get_device_properties(cuda_index)
+            bus = f"{p.pci_domain_id:08x}:{p.pci_bus_id:02x}:{p.pci_device_id:02x}.0"
+            self.nv, self.h = pynvml, pynvml.nvmlDeviceGetHandleByPciBusId(bus.encode())
+            all_links = 0xFFFFFFFF
+            self.fields = [(pynvml.NVML_FI_DEV_NVLINK_THROUGHPUT_DATA_RX, all_links),
+                           (pynvml.NVML_FI_DEV_NVLINK_THROUGHPUT_DATA_TX, all_links)]
+        except Exception as e:  # noqa: BLE001
+            self.h, self.why = None, f"{type(e).__name__}: {e}"
 
     def read(self):
         if self.h is None:
@@ -206,10 +210,12 @@ class NvlinkCounters:
             out = []
             for v in vals:
                 if v.nvmlReturn != 0:
+                    self.why = f"nvmlDeviceGetFieldValues: nvmlReturn {v.nvmlReturn}"
                     return None
-                out.append(int(v.value.ullVal) * 1024)
+                out.append(int(v.value.ullVal) * 1024)          # the counters tick in KiB
             return out          # [rx bytes, tx bytes]
-        except Exception:  # noqa: BLE001
+        except Exception as e:  # noqa: BLE001
+            self.why = f"{type(e).__name__}: {e}"
             return None
 
 
@@ -654,7 +660,7 @@ def section_item_sharded(sb, run, replica, items, off, ts, batches, d_batches, B
                               "measured_tx_bytes_per_query": round((c1[1] - c0[1]) / n_q, 1),
                               "source": "NVML NVLINK_THROUGHPUT_DATA_RX/TX of this rank's GPU around warm-up + timed steps"})
     else:
-        sec["nvlink"]["measured_rx_bytes_per_query"] = None
+        sec["nvlink"].update({"measured_rx_bytes_per_query": None, "why": nvl.why})
     # parity: sharded vs replica on the whole first timed batch, every rank
     out2 = run.device_buffers(B)
     run.launch(gix, d_batches[W], B, out)

@@ -5,7 +5,7 @@ import os
 import numpy as np
 import pytest
 
-from util import csr, evaluator_queries, random_index_data, read_test_sessions, same_modulo_ties
+from util import csr, evaluator_queries, mrr_hitrate_at, random_index_data, read_test_sessions, same_modulo_ties
 
 pytestmark = pytest.mark.gpu
 
@@ -207,13 +207,66 @@ def test_synthetic_config2_batch1024(sb, oracle):
     queries = [list(map(int, q_items[q_off[i]:q_off[i + 1]])) for i in range(1024)]
     ids, sc, cnt = _assert_batch_equal(sb, gix, oix, queries, 288, 1502, 21)
     assert (cnt == 21).mean() > 0.95
-    # faithful restatement: scores within 1e-5 (north-star tolerance) wherever the neighbour set is tie-free
-    close = 0
-    for q in range(0, 1024, 8):
+    # The faithful restatement of the Rust code (heaps + hash maps, mode 0) against the kernel's canonical order.  At
+    # k < m the reference keeps "the k best" through a heap whose tie handling depends on hashbrown's iteration order
+    # (vmis_index.rs:394-412); single-item sessions are ALL ties there (every candidate has similarity 1), so only the
+    # sessions where the boundary is tie-free can agree exactly; a different choice among tied neighbours shifts the
+    # scores (a few percent) even where the ranked ids coincide.  Measured on this data (bench.py prints the same
+    # figures for config 3): ~14 % identical ranked lists, ~26 % identical top-21 sets, mean set overlap@21 0.88.  The
+    # score tolerance proper (1e-5) is asserted where ties cannot interfere: test_faithful_agreement_without_boundary_ties.
+    same_list = same_set = 0
+    overlap = []
+    qs = list(range(0, 1024, 2))
+    for q in qs:
         fi, fs = oix.predict(queries[q], 288, 1502, 21, mode=0)
-        if len(fi) == cnt[q] and np.allclose(fs, sc[q, :cnt[q]], rtol=1e-5, atol=0):
-            close += 1
-    assert close >= 1   # single-item queries are all-tie at the k boundary (unpinned in the reference)
+        gi, gs = ids[q, :cnt[q]], sc[q, :cnt[q]]
+        a, b = set(gi.tolist()), set(fi.tolist())
+        overlap.append(len(a & b) / max(1, max(len(a), len(b))))
+        same_set += a == b
+        same_list += len(fi) == len(gi) and bool(np.array_equal(fi, gi))
+    print(f"canonical vs faithful on {len(qs)} sessions: same ranked list {same_list}, same top-21 set {same_set}, "
+          f"mean overlap@21 {np.mean(overlap):.3f}")
+    assert same_list >= len(qs) // 20 and same_set >= len(qs) // 8 and np.mean(overlap) >= 0.8
+
+
+def test_faithful_agreement_without_boundary_ties(sb, oracle):
+    """Where the reference's result does not depend on unpinned tie order — k >= m, unique timestamps — the faithful
+    restatement and the kernel must agree on the ranked ids (modulo exact-score ties) and on the scores to 1e-5."""
+    items, off, ts = sb.synth_sessions(42, 50_000, 193_000)
+    gix = sb.VMISIndex.from_sessions(items, off, ts, 300, 34, 2.0, device=0)
+    oix = oracle.OracleIndex.from_sessions(items, off, ts, 300, 34, 2.0)
+    q_items, q_off = sb.synth_queries(47, 50_000, 512, 4)
+    ids, sc, cnt = sb.predict_batch(gix, (q_items, q_off), 300, 300, 21)
+    agree = 0
+    for q in range(512):
+        fi, fs = oix.predict(q_items[q_off[q]:q_off[q + 1]], 300, 300, 21, mode=0)
+        assert len(fi) == cnt[q]
+        gs = sc[q, :cnt[q]]
+        # same scores position by position (ties may permute ids inside a tie class, never scores)
+        assert np.allclose(np.sort(fs)[::-1], gs, rtol=1e-5, atol=0)
+        agree += bool(np.array_equal(fi, ids[q, :cnt[q]]))
+        # ids equal as sets except inside the last tie class, which the cut at 21 may split differently
+        last = gs[-1] if cnt[q] else 0.0
+        a = {int(i) for i, s_ in zip(ids[q, :cnt[q]], gs) if s_ > last * (1 + 1e-12)}
+        b = {int(i) for i, s_ in zip(fi, fs) if s_ > last * (1 + 1e-12)}
+        assert a == b
+    assert agree >= 256
+
+
+def test_toy_quality_faithful_vs_kernel(sb, oracle, toy, toy_dir):
+    """README HPO optimum on the toy data (k=288, m=1502, last 4 items): MRR@20 / HitRate@20 of the kernel next to the
+    faithful restatement — the distance a user switching from the reference would see (vmis_index.rs:394-412,
+    mod.rs:185-212 leave the order of ties to hashbrown)."""
+    gix, oix, tests = toy
+    queries, rest = evaluator_queries(tests, 4)
+    ids, sc, cnt = sb.predict_batch(gix, queries, 288, 1502, 21)
+    g_recs = [ids[q, :cnt[q]].tolist() for q in range(len(queries))]
+    f_recs = [oix.predict(q, 288, 1502, 21, mode=0)[0].tolist() for q in queries]
+    g_mrr, g_hr = mrr_hitrate_at(g_recs, rest)
+    f_mrr, f_hr = mrr_hitrate_at(f_recs, rest)
+    overlap = np.mean([len(set(a) & set(b)) / max(1, max(len(a), len(b))) for a, b in zip(g_recs, f_recs)])
+    print(f"toy k=288 m=1502: kernel MRR@20 {g_mrr:.4f} HR@20 {g_hr:.4f} | faithful {f_mrr:.4f} {f_hr:.4f} | overlap@21 {overlap:.3f}")
+    assert abs(g_mrr - f_mrr) <= 0.006 and abs(g_hr - f_hr) <= 0.012 and overlap >= 0.85
 
 
 def test_device_api_and_stats(sb, oracle):
@@ -309,6 +362,74 @@ def test_full_size_properties_config3(sb, oracle):
     # how_many prefix property: top-5 is the prefix of top-21; k/m monotone sanity on counts
     ids5, sc5, cnt5 = sb.predict_batch(gix, (q_items, q_off), 288, 1502, 5)
     assert np.array_equal(ids5, ids[:, :5] * (np.arange(5)[None, :] < cnt5[:, None]))
+
+
+def test_full_size_config3_vs_oracle(sb, oracle):
+    """BASELINE config 3 at FULL size against the canonical oracle: 60 M interactions / 1.76 M items, 16 384 evolving
+    sessions, k=288, m=1502 — ids, order, f64 score bits and counts identical.  (Host-generated sessions so that the
+    oracle sees the same data; the device-generated index of the same seed must then answer identically too.)"""
+    items, off, ts = sb.synth_sessions(42, 1_760_000, 11_556_000)
+    assert len(items) == 60_017_474
+    gix = sb.VMISIndex.from_sessions(items, off, ts, 1502, 34, 2.0, device=0)
+    oix = oracle.OracleIndex.from_sessions(items, off, ts, 1502, 34, 2.0)
+    q_items, q_off = sb.synth_queries(4242, 1_760_000, 1 << 14, 4)
+    ids, sc, cnt = sb.predict_batch(gix, (q_items, q_off), 288, 1502, 21)
+    oids, osc, ocnt, _, _ = oix.predict_batch(q_items, q_off, 288, 1502, 21, mode=1, threads=os.cpu_count() or 8)
+    assert np.array_equal(cnt, ocnt) and np.array_equal(ids, oids) and np.array_equal(sc, osc)
+    del oix
+    dix = sb.VMISIndex.synth(42, 1_760_000, 11_556_000, 1502, 34, 2.0)
+    ids2, sc2, cnt2 = sb.predict_batch(dix, (q_items, q_off), 288, 1502, 21)
+    assert np.array_equal(cnt, cnt2) and np.array_equal(ids, ids2) and np.array_equal(sc, sc2)
+
+
+def test_config4_size_sharded_equals_unsharded(sb):
+    """BASELINE config 4 size (582 M interactions / 6.5 M items, device-generated): the index with its postings split
+    into two item shards (cross-attached by pointer on one GPU — the layout of config 5) answers 65 536 evolving
+    sessions exactly like the unsharded index."""
+    n_items, n_sessions = 6_500_000, 112_100_000
+    ref = sb.VMISIndex.synth(42, n_items, n_sessions, 1502, 34, 2.0)
+    assert ref.stats()["n_pairs_kept"] > 580_000_000
+    q_items, q_off = sb.synth_queries(99, n_items, 1 << 16, 4)
+    ids, sc, cnt = sb.predict_batch(ref, (q_items, q_off), 288, 1502, 21)
+    assert (cnt == 21).mean() > 0.9
+    ref.close()
+    shards = [sb.VMISIndex.synth(42, n_items, n_sessions, 1502, 34, 2.0, 0, s, 2) for s in range(2)]
+    shards[0].attach_shard_ptr(1, shards[1].shard_ptr())
+    shards[1].attach_shard_ptr(0, shards[0].shard_ptr())
+    for sh in shards:
+        ids2, sc2, cnt2 = sb.predict_batch(sh, (q_items, q_off), 288, 1502, 21)
+        assert np.array_equal(cnt, cnt2) and np.array_equal(ids, ids2) and np.array_equal(sc, sc2)
+
+
+def test_device_api_flags_over_long_sessions(sb):
+    """vmis_predict_batch_device cannot reject a launch: a session beyond VMIS_MAX_SESSION_LEN comes back with the
+    sentinel count; the host API refuses the same batch up front (VMIS_ERR_LIMIT)."""
+    torch = pytest.importorskip("torch")
+    gix = sb.VMISIndex.synth(42, 20_000, 60_000, 1502, 34, 2.0)
+    good_items, good_off = sb.synth_queries(43, 20_000, 3, 4)
+    long_session = np.arange(1, 131, dtype=np.uint64)
+    q_items = np.concatenate([good_items[:good_off[1]], long_session, good_items[good_off[1]:]])
+    q_off = np.concatenate([[0, good_off[1]], good_off[1:] + 130]).astype(np.uint32)
+    with pytest.raises(sb.VmisError) as e:
+        sb.predict_batch(gix, (q_items, q_off), 288, 1502, 21)
+    assert e.value.code == -4
+    dev = torch.device("cuda:0")
+    n_q, n = 4, 21
+    d_items = torch.from_numpy(q_items.view(np.int64)).to(dev)
+    d_off = torch.from_numpy(q_off.view(np.int32)).to(dev)
+    d_ids = torch.zeros((n_q, n), dtype=torch.int64, device=dev)
+    d_sc = torch.zeros((n_q, n), dtype=torch.float64, device=dev)
+    d_cnt = torch.zeros(n_q, dtype=torch.int32, device=dev)
+    lib = sb.load_library()
+    rc = lib.vmis_predict_batch_device(gix.handle, d_items.data_ptr(), d_off.data_ptr(), n_q, 288, 1502, n, 0,
+                                       d_ids.data_ptr(), d_sc.data_ptr(), d_cnt.data_ptr(), None,
+                                       C.c_void_p(torch.cuda.current_stream().cuda_stream))
+    assert rc == 0
+    torch.cuda.synchronize()
+    cnt = d_cnt.cpu().numpy().view(np.uint32)
+    assert cnt[1] == 0xFFFFFFFF and (d_ids[1] == 0).all()
+    ids, sc, c = sb.predict_batch(gix, (good_items, good_off), 288, 1502, n)
+    assert np.array_equal(cnt[[0, 2, 3]], c) and np.array_equal(d_ids.cpu().numpy().view(np.uint64)[[0, 2, 3]], ids)
 
 
 def test_chunked_host_api_matches_device_api(sb):
