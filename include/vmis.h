@@ -111,6 +111,15 @@ void vmis_sessions_free(vmis_sessions_t* sessions);
  * of training session s (any order; duplicates not allowed), sess_ts[s] its max timestamp. */
 vmis_index_t* vmis_index_from_sessions(const uint64_t* items, const uint64_t* sess_off, const uint32_t* sess_ts,
                                        size_t n_sessions, size_t m, size_t max_len, double idf_weighting, int device);
+/* The same with product attributes (item_to_product_attributes, vmis_index.rs:33,514-518): attr_items[i] gets the
+ * flags attr_flags[i] (VMIS_ATTR_FOR_SALE | VMIS_ATTR_ADULT; 0 = "no attributes", which fails the business rules of
+ * mod.rs:162-182).  Items not listed keep the CSV default {adult: false, for_sale: true}; attr_items == NULL is
+ * vmis_index_from_sessions.  (The dense order of the items is internal to the index, so the attributes travel as
+ * (external id, flags) pairs rather than as one positional array.) */
+vmis_index_t* vmis_index_from_sessions_attrs(const uint64_t* items, const uint64_t* sess_off, const uint32_t* sess_ts,
+                                             size_t n_sessions, size_t m, size_t max_len, double idf_weighting,
+                                             const uint64_t* attr_items, const uint8_t* attr_flags, size_t n_attrs,
+                                             int device);
 
 /* ---- item-sharded postings (BASELINE.json config 5; no counterpart in the reference, which replicates) ----
  * The item→sessions index is partitioned over the GPUs of one box: shard s of n holds the posting lists of the

@@ -432,6 +432,30 @@ bool dump_dev(FILE* f, const T* dev, uint64_t n) {
 }
 template <class T>
 bool slurp(FILE* f, std::vector<T>* v, uint64_t n) { v->resize(n); return std::fread(v->data(), sizeof(T), n, f) == n; }
+// FNV-1a (64 bit, 8 bytes at a time) over the arrays of a blob in file order
+struct Fnv {
+  uint64_t h = 0xcbf29ce484222325ull;
+  void add(const void* p, size_t bytes) {
+    const unsigned char* b = static_cast<const unsigned char*>(p);
+    size_t i = 0;
+    for (; i + 8 <= bytes; i += 8) { uint64_t w; std::memcpy(&w, b + i, 8); h = (h ^ w) * 0x100000001b3ull; }
+    for (; i < bytes; ++i) h = (h ^ b[i]) * 0x100000001b3ull;
+  }
+  template <class T> void add(const std::vector<T>& v) { add(v.data(), v.size() * sizeof(T)); }
+};
+uint64_t blob_checksum(const vmis::FlatIndex& F, const std::vector<uint32_t>& own) {
+  Fnv c;
+  c.add(F.item_key); c.add(F.item_hash); c.add(F.post_ref); c.add(own); c.add(F.sess_ref); c.add(F.sess_items);
+  c.add(F.idf); c.add(F.attr); c.add(F.rank_to_orig);
+  return c.h;
+}
+template <class T>
+bool dump_dev_sum(FILE* f, const T* dev, uint64_t n, Fnv* c) {
+  std::vector<T> h(n);
+  if (n && cudaMemcpy(h.data(), dev, n * sizeof(T), cudaMemcpyDeviceToHost) != cudaSuccess) return false;
+  c->add(h);
+  return std::fwrite(h.data(), sizeof(T), n, f) == n;
+}
 }  // namespace
 
 extern "C" {
@@ -449,6 +473,16 @@ vmis_index_t* vmis_index_from_sessions(const uint64_t* items, const uint64_t* se
   ix->sessions.ts.assign(sess_ts, sess_ts + n_sessions);
   ix->sessions.items.assign(items, items + sess_off[n_sessions]);
   return finish_index(std::move(ix), m, max_len, idf_weighting, device);
+}
+
+vmis_index_t* vmis_index_from_sessions_attrs(const uint64_t* items, const uint64_t* sess_off, const uint32_t* sess_ts,
+                                             size_t n_sessions, size_t m, size_t max_len, double idf_weighting,
+                                             const uint64_t* attr_items, const uint8_t* attr_flags, size_t n_attrs,
+                                             int device) {
+  if (n_attrs && (!attr_items || !attr_flags)) { fail(VMIS_ERR_ARG, "NULL attribute arrays"); return nullptr; }
+  vmis_index_t* ix = vmis_index_from_sessions(items, sess_off, sess_ts, n_sessions, m, max_len, idf_weighting, device);
+  if (ix && n_attrs && vmis_index_set_attributes(ix, attr_items, attr_flags, n_attrs) != VMIS_OK) { vmis_index_free(ix); return nullptr; }
+  return ix;
 }
 
 vmis_index_t* vmis_index_from_sessions_sharded(const uint64_t* items, const uint64_t* sess_off, const uint32_t* sess_ts,
@@ -594,38 +628,88 @@ int vmis_index_save(const vmis_index_t* ix, const char* path) {
   const vmis::IndexView& V = ix->view;
   BlobHeader h{};
   std::memcpy(h.magic, "VMISB200", 8);
-  h.version = 2; h.n_shards = V.n_shards; h.shard = ix->shard; h.m_build = V.m_build; h.max_len = V.max_len; h.m_carry = V.m_carry;
+  h.version = 3; h.n_shards = V.n_shards; h.shard = ix->shard; h.m_build = V.m_build; h.max_len = V.max_len; h.m_carry = V.m_carry;
   h.n_items = V.n_items; h.hash_cap = (uint64_t)V.item_hash_mask + 1; h.n_kept = V.n_kept;
   h.n_post_entries = ix->n_post_entries; h.n_sess_item_entries = ix->n_sess_item_entries;
   h.n_pairs_kept = ix->flat.n_pairs_kept; h.n_postings = ix->flat.n_postings; h.idf_weighting = ix->flat.idf_weighting;
-  bool ok = std::fwrite(&h, sizeof h, 1, f) == 1 && dump_dev(f, V.item_key, h.n_items) && dump_dev(f, V.item_hash, h.hash_cap) &&
-            dump_dev(f, V.post_ref, h.n_items) && dump_dev(f, V.post_shard[ix->shard], h.n_post_entries) &&
-            dump_dev(f, V.sess_ref, h.n_kept) && dump_dev(f, V.sess_items, h.n_sess_item_entries) &&
-            dump_dev(f, V.idf, h.n_items) && dump_dev(f, V.attr, h.n_items) && dump_dev(f, V.rank_to_orig, h.n_kept);
+  Fnv sum;
+  bool ok = std::fwrite(&h, sizeof h, 1, f) == 1 && dump_dev_sum(f, V.item_key, h.n_items, &sum) && dump_dev_sum(f, V.item_hash, h.hash_cap, &sum) &&
+            dump_dev_sum(f, V.post_ref, h.n_items, &sum) && dump_dev_sum(f, V.post_shard[ix->shard], h.n_post_entries, &sum) &&
+            dump_dev_sum(f, V.sess_ref, h.n_kept, &sum) && dump_dev_sum(f, V.sess_items, h.n_sess_item_entries, &sum) &&
+            dump_dev_sum(f, V.idf, h.n_items, &sum) && dump_dev_sum(f, V.attr, h.n_items, &sum) && dump_dev_sum(f, V.rank_to_orig, h.n_kept, &sum);
+  ok = ok && std::fwrite(&sum.h, 8, 1, f) == 1;
   ok = (std::fclose(f) == 0) && ok;
   if (!ok) return fail(VMIS_ERR_IO, "short write to %s", path);
   return VMIS_OK;
 }
 
+// Loads a blob written by vmis_index_save.  Nothing in the file is trusted: the header is checked against the file
+// size before anything is allocated, every offset / rank / item index is checked against the array it points into
+// (the kernel does no bounds checks), and version 3 blobs carry a checksum over the arrays.
 vmis_index_t* vmis_index_load(const char* path, int device) {
   g_err_code = 0;
   if (!path) { fail(VMIS_ERR_ARG, "path is NULL"); return nullptr; }
   FILE* f = std::fopen(path, "rb");
   if (!f) { fail(VMIS_ERR_IO, "cannot open %s", path); return nullptr; }
-  BlobHeader h{};
   std::unique_ptr<vmis_index> ix(new vmis_index());
-  vmis::FlatIndex& F = ix->flat;
+  BlobHeader h{};
   std::vector<uint32_t> own;
-  bool ok = std::fread(&h, sizeof h, 1, f) == 1 && !std::memcmp(h.magic, "VMISB200", 8) && (h.version == 1 || h.version == 2) &&
-            h.n_shards >= 1 && h.n_shards <= (uint32_t)vmis::kMaxShards && h.shard < h.n_shards;
-  ok = ok && slurp(f, &F.item_key, h.n_items) && slurp(f, &F.item_hash, h.hash_cap) && slurp(f, &F.post_ref, h.n_items) &&
-       slurp(f, &own, h.n_post_entries) && slurp(f, &F.sess_ref, h.n_kept) && slurp(f, &F.sess_items, h.n_sess_item_entries) &&
-       slurp(f, &F.idf, h.n_items) && slurp(f, &F.attr, h.n_items) && slurp(f, &F.rank_to_orig, h.n_kept);
-  std::fclose(f);
-  if (!ok) { fail(VMIS_ERR_IO, "%s is not a VMIS index blob (or is truncated)", path); return nullptr; }
-  if (h.version == 1) h.m_carry = h.m_build;
-  F.n_pairs_kept = h.n_pairs_kept; F.n_postings = h.n_postings; F.m_build = h.m_build; F.m_carry = h.m_carry; F.max_len = h.max_len;
-  F.idf_weighting = h.idf_weighting; F.n_shards = h.n_shards;
+  const char* why = nullptr;
+  try {
+    vmis::FlatIndex& F = ix->flat;
+    std::fseek(f, 0, SEEK_END);
+    const long long fsize = std::ftell(f);
+    std::fseek(f, 0, SEEK_SET);
+    bool ok = std::fread(&h, sizeof h, 1, f) == 1 && !std::memcmp(h.magic, "VMISB200", 8) && h.version >= 1 && h.version <= 3;
+    if (!ok) why = "not a VMIS index blob";
+    if (ok && !(h.n_shards >= 1 && h.n_shards <= (uint32_t)vmis::kMaxShards && h.shard < h.n_shards)) { ok = false; why = "bad shard fields"; }
+    if (ok && !(h.n_items < 0xFFFFFFFFull && h.n_kept < 0x80000000ull && h.hash_cap <= (1ull << 33) && h.n_post_entries < (1ull << 40) &&
+                h.n_sess_item_entries < (1ull << 40))) { ok = false; why = "counts out of range"; }
+    if (ok && !((h.hash_cap & (h.hash_cap - 1)) == 0 && h.hash_cap > h.n_items)) { ok = false; why = "item hash capacity is not a power of two above the item count"; }
+    if (ok && (h.version >= 2 ? h.m_carry : h.m_build) > h.m_build) { ok = false; why = "m_carry above m_build"; }
+    const unsigned long long expect = sizeof h + h.n_items * 8 + h.hash_cap * sizeof(vmis::ItemHashEntry) + h.n_items * sizeof(uint2) +
+                                      h.n_post_entries * 4 + h.n_kept * sizeof(uint2) + h.n_sess_item_entries * 4 + h.n_items * 8 +
+                                      h.n_items + h.n_kept * 4 + (h.version >= 3 ? 8 : 0);
+    if (ok && (unsigned long long)fsize != expect) { ok = false; why = "file size does not match the header (truncated or corrupt)"; }
+    ok = ok && slurp(f, &F.item_key, h.n_items) && slurp(f, &F.item_hash, h.hash_cap) && slurp(f, &F.post_ref, h.n_items) &&
+         slurp(f, &own, h.n_post_entries) && slurp(f, &F.sess_ref, h.n_kept) && slurp(f, &F.sess_items, h.n_sess_item_entries) &&
+         slurp(f, &F.idf, h.n_items) && slurp(f, &F.attr, h.n_items) && slurp(f, &F.rank_to_orig, h.n_kept);
+    if (ok && h.version >= 3) {
+      uint64_t stored = 0;
+      ok = std::fread(&stored, 8, 1, f) == 1;
+      if (ok && stored != blob_checksum(F, own)) { ok = false; why = "checksum mismatch"; }
+    }
+    if (ok) {
+      // structure: everything the kernel dereferences stays inside its array
+      for (size_t d = 1; d < F.item_key.size() && ok; ++d) ok = F.item_key[d - 1] < F.item_key[d];
+      if (!ok) why = "item dictionary is not strictly ascending";
+      for (size_t i = 0; i < F.item_hash.size() && ok; ++i) ok = F.item_hash[i].val == vmis::kEmpty || F.item_hash[i].val < h.n_items;
+      if (!ok && !why) why = "item hash entry out of range";
+      for (size_t d = 0; d < F.post_ref.size() && ok; ++d) {
+        ok = F.post_ref[d].y <= h.m_build;
+        if (ok && d % h.n_shards == h.shard) ok = (uint64_t)F.post_ref[d].x * 4 + F.post_ref[d].y <= h.n_post_entries;
+      }
+      if (!ok && !why) why = "posting list reference out of range";
+      for (size_t i = 0; i < own.size() && ok; ++i) ok = own[i] == vmis::kEmpty || own[i] < h.n_kept;
+      if (!ok && !why) why = "posting (session rank) out of range";
+      for (size_t r = 0; r < F.sess_ref.size() && ok; ++r)
+        ok = F.sess_ref[r].y <= h.max_len && (uint64_t)F.sess_ref[r].x * 4 + F.sess_ref[r].y <= h.n_sess_item_entries;
+      if (!ok && !why) why = "session item list reference out of range";
+      for (size_t i = 0; i < F.sess_items.size() && ok; ++i) ok = F.sess_items[i] == vmis::kEmpty || F.sess_items[i] < h.n_items;
+      if (!ok && !why) why = "session item out of range";
+      if (ok && (F.sess_items.size() & 3)) { ok = false; why = "session item array is not padded to 16 bytes"; }
+    }
+    std::fclose(f); f = nullptr;
+    if (!ok) { fail(VMIS_ERR_IO, "%s: %s", path, why ? why : "truncated"); return nullptr; }
+    if (h.version == 1) h.m_carry = h.m_build;
+    F.n_pairs_kept = h.n_pairs_kept; F.n_postings = h.n_postings; F.m_build = h.m_build; F.m_carry = h.m_carry; F.max_len = h.max_len;
+    F.idf_weighting = h.idf_weighting; F.n_shards = h.n_shards;
+  } catch (const std::exception& e) {
+    if (f) std::fclose(f);
+    fail(VMIS_ERR_IO, "%s: %s", path, e.what());
+    return nullptr;
+  }
+  vmis::FlatIndex& F = ix->flat;
   ix->shard = h.shard; ix->n_sessions_kept = h.n_kept; ix->device = device;
   if (select_device(device, &ix->sm_count) != VMIS_OK) return nullptr;
   vmis::IndexView& V = ix->view;

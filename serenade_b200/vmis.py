@@ -59,6 +59,7 @@ def load_library():
         "vmis_sessions_view": (i32, [vp, C.POINTER(_u64p), C.POINTER(_u64p), C.POINTER(_u32p), C.POINTER(sz)]),
         "vmis_sessions_free": (None, [vp]),
         "vmis_index_from_sessions": (vp, [_u64p, _u64p, _u32p, sz, sz, sz, f64, i32]),
+        "vmis_index_from_sessions_attrs": (vp, [_u64p, _u64p, _u32p, sz, sz, sz, f64, _u64p, _u8p, sz, i32]),
         "vmis_index_from_sessions_sharded": (vp, [_u64p, _u64p, _u32p, sz, sz, sz, f64, i32, u32, u32]),
         "vmis_index_from_device_sessions": (vp, [vp, vp, vp, sz, sz, sz, f64, i32, u32, u32]),
         "vmis_index_synth": (vp, [u64, u64, u64, sz, sz, f64, i32, u32, u32]),
@@ -112,7 +113,7 @@ def load_library():
 
 
 EXPORTED_SYMBOLS = ("vmis_index_from_csv", "vmis_index_from_csv_ex", "vmis_sessions_from_csv", "vmis_sessions_view",
-                    "vmis_sessions_free", "vmis_index_from_sessions",
+                    "vmis_sessions_free", "vmis_index_from_sessions", "vmis_index_from_sessions_attrs",
                     "vmis_index_from_sessions_sharded", "vmis_index_export_shard", "vmis_index_attach_shard",
                     "vmis_index_attach_shard_ptr", "vmis_index_shard_ptr", "vmis_index_from_device_sessions",
                     "vmis_index_synth", "vmis_index_from_avro", "vmis_index_from_avro_sharded", "vmis_index_from_parts",
@@ -163,12 +164,20 @@ class VMISIndex:
                                             float(idf_weighting), max_len, device))
 
     @classmethod
-    def from_sessions(cls, items, sess_off, sess_ts, m_most_recent_sessions, max_len, idf_weighting, device=0):
-        """prepare_hashmap (vmis_index.rs:422) + struct assembly (:75-82)."""
+    def from_sessions(cls, items, sess_off, sess_ts, m_most_recent_sessions, max_len, idf_weighting, device=0,
+                      attributes=None):
+        """prepare_hashmap (vmis_index.rs:422) + struct assembly (:75-82).  attributes: optional (item ids, flags)."""
         L = load_library()
         items = np.ascontiguousarray(items, dtype=np.uint64)
         sess_off = np.ascontiguousarray(sess_off, dtype=np.uint64)
         sess_ts = np.ascontiguousarray(sess_ts, dtype=np.uint32)
+        if attributes is not None:
+            a_items = np.ascontiguousarray(attributes[0], dtype=np.uint64)
+            a_flags = np.ascontiguousarray(attributes[1], dtype=np.uint8)
+            return cls(L.vmis_index_from_sessions_attrs(_p(items, C.c_uint64), _p(sess_off, C.c_uint64),
+                                                        _p(sess_ts, C.c_uint32), len(sess_ts), m_most_recent_sessions,
+                                                        max_len, float(idf_weighting), _p(a_items, C.c_uint64),
+                                                        _p(a_flags, C.c_uint8), len(a_items), device))
         return cls(L.vmis_index_from_sessions(_p(items, C.c_uint64), _p(sess_off, C.c_uint64),
                                               _p(sess_ts, C.c_uint32), len(sess_ts), m_most_recent_sessions, max_len,
                                               float(idf_weighting), device))

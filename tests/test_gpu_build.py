@@ -122,3 +122,30 @@ def test_save_load_roundtrip(sb, tmp_path):
     with pytest.raises(sb.VmisError) as e:
         sb.VMISIndex.load(str(bad))
     assert e.value.code == -2
+
+
+def test_blob_loader_rejects_corrupt_files(sb, tmp_path):
+    """nothing in a blob is trusted — absurd counts, truncation, flipped payload bytes and out-of-range
+    references all fail with VMIS_ERR_IO instead of aborting the process or handing the kernel a bad pointer."""
+    items, off, ts = sb.synth_sessions(42, 2000, 8000)
+    ix = sb.VMISIndex.from_sessions(items, off, ts, 300, 34, 2.0, device=0)
+    path = str(tmp_path / "index.vmis")
+    ix.save(path)
+    blob = bytearray(open(path, "rb").read())
+    # header layout: magic[8], 6 x u32, 7 x u64, f64
+
+    def try_load(data, what):
+        p = tmp_path / "c.vmis"
+        p.write_bytes(bytes(data))
+        with pytest.raises(sb.VmisError) as e:
+            sb.VMISIndex.load(str(p))
+        assert e.value.code == -2, what
+
+    huge = bytearray(blob); huge[32:40] = (1 << 60).to_bytes(8, "little")            # n_items = 2^60
+    try_load(huge, "huge n_items")
+    try_load(blob[:len(blob) // 2], "truncated")
+    cap = bytearray(blob); cap[40:48] = (int.from_bytes(blob[40:48], "little") - 1).to_bytes(8, "little")
+    try_load(cap, "hash capacity not a power of two")
+    flip = bytearray(blob); flip[len(blob) // 2] ^= 0x40                                # payload bit flip → checksum
+    try_load(flip, "bit flip")
+    assert sb.VMISIndex.load(path).stats()["n_items"] == ix.stats()["n_items"]          # the intact file still loads

@@ -26,6 +26,53 @@ def test_header_symbols_are_exported(sb):
     assert b"sm_100a" in sb.load_library().vmis_version()
 
 
+def test_rust_binding_matches_header():
+    """bindings/rust/src/lib.rs cannot be compiled here (no Rust toolchain): every function of its extern "C" block
+    must be declared in include/vmis.h with the same number of parameters and be exported by the library."""
+    hdr = re.sub(r"/\*.*?\*/", "", open(os.path.join(ROOT, "include", "vmis.h")).read(), flags=re.S)
+    c_decl = {m.group(1): len([a for a in m.group(2).split(",") if a.strip() and a.strip() != "void"])
+              for m in re.finditer(r"\b(vmis_[a-z_0-9]+)\s*\(([^)]*)\)\s*;", hdr)}
+    rs = open(os.path.join(ROOT, "bindings", "rust", "src", "lib.rs")).read()
+    block = rs[rs.index('extern "C" {'):]
+    block = block[:block.index("\n}\n")]
+    rust_decl = {m.group(1): len([a for a in m.group(2).split(",") if ":" in a])
+                 for m in re.finditer(r"pub fn (vmis_[a-z_0-9]+)\(([^)]*)\)", block, flags=re.S)}
+    assert len(rust_decl) >= 11
+    lib = C.CDLL(os.path.join(ROOT, "serenade_b200", "libvmis_b200.so"))
+    for name, n_args in rust_decl.items():
+        assert name in c_decl, f"{name} is not declared in include/vmis.h"
+        assert c_decl[name] == n_args, f"{name}: {n_args} parameters in Rust, {c_decl[name]} in C"
+        assert hasattr(lib, name)
+    # the trait method must bridge to the handle's attributes, not to a Rust-side map (similarity_indexed.rs:23)
+    assert "vmis_find_attributes(self.h" in rs
+
+
+def test_index_from_sessions_with_attributes(sb, oracle):
+    """vmis_index_from_sessions_attrs: attributes as (external id, flags) pairs; unlisted items keep the CSV default"""
+    items, off, ts = random_index_data(np.random.default_rng(3), 200, 40)
+    ids = np.unique(items)[:5]
+    flags = np.array([sb.vmis.ATTR_FOR_SALE | sb.vmis.ATTR_ADULT, 0, sb.vmis.ATTR_FOR_SALE, sb.vmis.ATTR_ADULT, 0], dtype=np.uint8)
+    hix = sb.VMISIndex.from_sessions(items, off, ts, 10, 8, 1.0, device=sb.DEVICE_NONE, attributes=(ids, flags))
+    assert hix.find_attributes(int(ids[0])) == {"is_for_sale": True, "is_adult": True}
+    assert hix.find_attributes(int(ids[1])) is None
+    assert hix.find_attributes(int(ids[2])) == {"is_for_sale": True, "is_adult": False}
+    assert hix.find_attributes(int(ids[3])) == {"is_for_sale": False, "is_adult": True}
+    other = int(np.unique(items)[7])
+    assert hix.find_attributes(other) == {"is_for_sale": True, "is_adult": False}      # vmis_index.rs:514-518
+
+
+def test_error_code_is_cleared_by_the_next_successful_call(sb):
+    """vmis_last_error_code() used to stick after a failure"""
+    items, off, ts = random_index_data(np.random.default_rng(1), 50, 10)
+    hix = sb.VMISIndex.from_sessions(items, off, ts, 10, 8, 1.0, device=sb.DEVICE_NONE)
+    lib = sb.load_library()
+    with pytest.raises(KeyError):
+        hix.idf(0xDEADBEEFDEADBEEF)
+    assert lib.vmis_last_error_code() != 0
+    assert hix.idf(int(items[0])) > 0
+    assert lib.vmis_last_error_code() == 0
+
+
 def test_library_has_no_oracle_dependency():
     """the product must not link or load anything under oracle/"""
     import subprocess
