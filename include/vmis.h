@@ -71,6 +71,7 @@ typedef struct vmis_prebuilt_info {
   uint64_t item_records, session_records;  /* records decoded (before "last record of a key wins")             */
   uint64_t lists_reordered;                /* posting lists not in (timestamp desc, session idx desc) order     */
   uint64_t duplicate_postings;             /* repeated session ids dropped from posting lists                   */
+  uint64_t pruned_postings;                /* postings dropped because their session exceeds max_session_len    */
   uint32_t m_carry;                        /* m <= m_carry: first-match positions are carried through the list  */
                                            /* merges; larger m scans the item lists like mod.rs:133-138         */
   uint32_t prebuilt;                       /* 1 = the handle was made from pre-computed parts                   */
@@ -157,6 +158,14 @@ vmis_index_t* vmis_index_synth(uint64_t seed, uint64_t n_items, uint64_t n_sessi
  * fails the load.  VMIS_DEVICE_NONE gives a host-only handle (accessors only). */
 vmis_index_t* vmis_index_from_avro(const char* base_path, int device);
 vmis_index_t* vmis_index_from_avro_sharded(const char* base_path, int device, uint32_t shard, uint32_t n_shards);
+/* max_session_len > 0 additionally drops the sessions with more items from every posting list — what prepare_hashmap
+ * does for a CSV index at the 99.5th length percentile (vmis_index.rs:67,452).  The offline Avro index keeps every
+ * session (the reference's production statistics name sessions of 9408 events, vmis_index.rs:116-126); one such
+ * session makes the worst-case score table of a query k x 9408 entries, so a serving index should be loaded with a
+ * bound (0 = keep everything; queries then fail with VMIS_ERR_LIMIT and a message naming this option once
+ * k x longest session exceeds the kernel's workspace bound). */
+vmis_index_t* vmis_index_from_avro_ex(const char* base_path, int device, uint32_t shard, uint32_t n_shards,
+                                      size_t max_session_len);
 /* The same from arrays in memory: item i has ids item_ids[i], posting list post_sessions[post_off[i] ..
  * post_off[i+1]) (session indices), idf[i] and attr[i] (VMIS_ATTR_* bits; NULL = for sale, not adult); sessions
  * are dense by session index like session_to_items_sorted / session_to_max_time_stamp (:28-35). */
@@ -164,6 +173,10 @@ vmis_index_t* vmis_index_from_parts(const uint64_t* item_ids, const uint64_t* po
                                     const double* idf, const uint8_t* attr_or_null, size_t n_items, const uint64_t* items,
                                     const uint64_t* sess_off, const uint32_t* sess_ts, size_t n_sessions, int device,
                                     uint32_t shard, uint32_t n_shards);
+vmis_index_t* vmis_index_from_parts_ex(const uint64_t* item_ids, const uint64_t* post_off, const uint32_t* post_sessions,
+                                       const double* idf, const uint8_t* attr_or_null, size_t n_items, const uint64_t* items,
+                                       const uint64_t* sess_off, const uint32_t* sess_ts, size_t n_sessions, int device,
+                                       uint32_t shard, uint32_t n_shards, size_t max_session_len);
 int vmis_index_prebuilt_info(const vmis_index_t* index, vmis_prebuilt_info_t* out);
 /* The reverse direction: writes the index in that on-disk format (the reference computes it offline with Spark), so an
  * index built on the GPU can be served by the reference: <base_path>/itemindex/part-NNNNN.avro and

@@ -45,7 +45,7 @@ struct CallCtx {
   cudaEvent_t done = nullptr;      // last use of ws / buf
   void* buf = nullptr; size_t buf_cap = 0;
   void* ws = nullptr; size_t ws_cap = 0;
-  uint32_t ws_grid = 0, ws_gtab_cap = 0;   // geometry the workspace tables were initialised for
+  uint32_t ws_grid = 0, ws_gtab_cap = 0, ws_gtab_huge = 0;   // geometry the workspace tables were initialised for
   void* pinned = nullptr; size_t pinned_cap = 0;   // host staging of small batches (one copy each way)
   void* pinned_dev = nullptr;                      // device view of `pinned` (mapped: tiny batches skip the copies)
   ~CallCtx() {
@@ -266,9 +266,9 @@ int check_common(const vmis_index* ix, uint32_t k, uint32_t m, vmis::LaunchPlan*
     if (!ix->view.post_shard[s2]) return fail(VMIS_ERR_ARG, "posting shard %u of %u is not attached", s2, ix->view.n_shards);
   if (ix->view.n_kept >= 0x80000000u)     // the list merges compare time ranks as signed numbers (kEmpty sentinel = -1)
     return fail(VMIS_ERR_LIMIT, "%u kept sessions; the kernel handles fewer than 2^31", ix->view.n_kept);
-  const int rc = vmis::plan_launch(ix->view, k, m, ix->sm_count, plan);
-  if (rc != VMIS_OK)
-    return fail(rc, "k=%u / m=%u beyond kernel limits (k <= %u, m <= %u and shared memory)", k, m, vmis::kMaxK, vmis::kMaxM);
+  std::string why;
+  const int rc = vmis::plan_launch(ix->view, k, m, ix->sm_count, plan, &why);
+  if (rc != VMIS_OK) return fail(rc, "%s", why.c_str());
   return VMIS_OK;
 }
 
@@ -279,9 +279,9 @@ int run_device(vmis_index* ix, CallCtx* c, const vmis::PredictArgs& args, const 
   if (rc) return rc;
   CU_TRY(cudaStreamWaitEvent(stream, c->done, 0));
   const vmis::Workspace ws = vmis::carve_workspace(c->ws, plan);
-  if (c->ws_cap != old_cap || c->ws_grid != plan.grid || c->ws_gtab_cap != plan.gtab_cap) {
+  if (c->ws_cap != old_cap || c->ws_grid != plan.grid || c->ws_gtab_cap != plan.gtab_cap || c->ws_gtab_huge != plan.gtab_huge) {
     CU_TRY(vmis::init_workspace(ws, stream));
-    c->ws_grid = plan.grid; c->ws_gtab_cap = plan.gtab_cap;
+    c->ws_grid = plan.grid; c->ws_gtab_cap = plan.gtab_cap; c->ws_gtab_huge = plan.gtab_huge;
   }
   CU_TRY(vmis::launch_predict(ix->view, args, plan, ws, stream));
   CU_TRY(cudaEventRecord(c->done, stream));
@@ -529,8 +529,26 @@ vmis_index_t* vmis_index_synth(uint64_t seed, uint64_t n_items, uint64_t n_sessi
 }
 
 // ---- pre-computed index (VMISIndex::new, vmis_index.rs:85-313): posting lists, idf and attributes are taken as given ----
-static vmis_index_t* finish_prebuilt(std::unique_ptr<vmis_index> ix, vmis::PrebuiltIndex& P, int device, uint32_t shard, uint32_t n_shards) {
+static vmis_index_t* finish_prebuilt(std::unique_ptr<vmis_index> ix, vmis::PrebuiltIndex& P, int device, uint32_t shard, uint32_t n_shards,
+                                     size_t max_session_len = 0) {
   if (n_shards == 0 || shard >= n_shards) { fail(VMIS_ERR_ARG, "shard %u out of range [0,%u)", shard, n_shards); return nullptr; }
+  if (max_session_len) {
+    // drop the sessions above the bound from the posting lists, as prepare_hashmap does for a CSV index
+    // (vmis_index.rs:452); they stay in the host mirror (items_for_session) but can no longer become neighbours
+    const vmis::Sessions& S = P.sessions;
+    std::vector<uint64_t> off(1, 0);
+    size_t w = 0;
+    for (size_t d = 0; d + 1 < P.post_off.size(); ++d) {
+      for (uint64_t e = P.post_off[d]; e < P.post_off[d + 1]; ++e) {
+        const uint32_t sid = P.post_sessions[e];
+        if (sid < S.size() && S.off[sid + 1] - S.off[sid] > max_session_len) { ++ix->prebuilt.pruned_postings; continue; }
+        P.post_sessions[w++] = sid;
+      }
+      off.push_back(w);
+    }
+    P.post_sessions.resize(w);
+    P.post_off.swap(off);
+  }
   vmis::PrebuiltInfo pi; std::string err;
   if (!vmis::build_flat_index_prebuilt(P, n_shards, &ix->flat, &pi, &err)) { fail(VMIS_ERR_ARG, "%s", err.c_str()); return nullptr; }
   ix->sessions.items.swap(P.sessions.items); ix->sessions.off.swap(P.sessions.off); ix->sessions.ts.swap(P.sessions.ts);
@@ -539,7 +557,7 @@ static vmis_index_t* finish_prebuilt(std::unique_ptr<vmis_index> ix, vmis::Prebu
   return upload_flat(std::move(ix), device, shard, n_shards);
 }
 
-vmis_index_t* vmis_index_from_avro_sharded(const char* base_path, int device, uint32_t shard, uint32_t n_shards) {
+vmis_index_t* vmis_index_from_avro_ex(const char* base_path, int device, uint32_t shard, uint32_t n_shards, size_t max_session_len) {
   g_err_code = 0;
   if (!base_path) { fail(VMIS_ERR_ARG, "path is NULL"); return nullptr; }
   std::unique_ptr<vmis_index> ix(new vmis_index());
@@ -547,15 +565,27 @@ vmis_index_t* vmis_index_from_avro_sharded(const char* base_path, int device, ui
   if (!vmis::read_index_from_avro(base_path, &P, &li, &err)) { fail(VMIS_ERR_IO, "%s", err.c_str()); return nullptr; }
   ix->prebuilt.item_files = li.item_files; ix->prebuilt.session_files = li.session_files;
   ix->prebuilt.item_records = li.item_records; ix->prebuilt.session_records = li.session_records;
-  return finish_prebuilt(std::move(ix), P, device, shard, n_shards);
+  return finish_prebuilt(std::move(ix), P, device, shard, n_shards, max_session_len);
 }
 
-vmis_index_t* vmis_index_from_avro(const char* base_path, int device) { return vmis_index_from_avro_sharded(base_path, device, 0, 1); }
+vmis_index_t* vmis_index_from_avro_sharded(const char* base_path, int device, uint32_t shard, uint32_t n_shards) {
+  return vmis_index_from_avro_ex(base_path, device, shard, n_shards, 0);
+}
+
+vmis_index_t* vmis_index_from_avro(const char* base_path, int device) { return vmis_index_from_avro_ex(base_path, device, 0, 1, 0); }
 
 vmis_index_t* vmis_index_from_parts(const uint64_t* item_ids, const uint64_t* post_off, const uint32_t* post_sessions,
                                     const double* idf, const uint8_t* attr_or_null, size_t n_items, const uint64_t* items,
                                     const uint64_t* sess_off, const uint32_t* sess_ts, size_t n_sessions, int device,
                                     uint32_t shard, uint32_t n_shards) {
+  return vmis_index_from_parts_ex(item_ids, post_off, post_sessions, idf, attr_or_null, n_items, items, sess_off, sess_ts, n_sessions,
+                                  device, shard, n_shards, 0);
+}
+
+vmis_index_t* vmis_index_from_parts_ex(const uint64_t* item_ids, const uint64_t* post_off, const uint32_t* post_sessions,
+                                       const double* idf, const uint8_t* attr_or_null, size_t n_items, const uint64_t* items,
+                                       const uint64_t* sess_off, const uint32_t* sess_ts, size_t n_sessions, int device,
+                                       uint32_t shard, uint32_t n_shards, size_t max_session_len) {
   g_err_code = 0;
   if (!item_ids || !post_off || !idf || !sess_off || !sess_ts || (!post_sessions && n_items && post_off[n_items] > 0) ||
       (!items && n_sessions && sess_off[n_sessions] > 0)) { fail(VMIS_ERR_ARG, "NULL index arrays"); return nullptr; }
@@ -570,7 +600,7 @@ vmis_index_t* vmis_index_from_parts(const uint64_t* item_ids, const uint64_t* po
   P.sessions.off.assign(sess_off, sess_off + n_sessions + 1);
   P.sessions.ts.assign(sess_ts, sess_ts + n_sessions);
   P.sessions.items.assign(items, items + sess_off[n_sessions]);
-  return finish_prebuilt(std::move(ix), P, device, shard, n_shards);
+  return finish_prebuilt(std::move(ix), P, device, shard, n_shards, max_session_len);
 }
 
 int vmis_index_prebuilt_info(const vmis_index_t* ix, vmis_prebuilt_info_t* out) {

@@ -35,11 +35,13 @@
 #include <atomic>
 #include <cstdio>
 #include <cstdlib>
+#include <string>
 
 namespace vmis {
 namespace {
 
 constexpr unsigned kFull = 0xFFFFFFFFu;
+constexpr unsigned long long kMaxWorkspaceBytes = 8ull << 30;   // overflow tables of one call context
 constexpr int kVT = 8;                       // merge-path items per thread per tile
 constexpr int kTile = kThreads * kVT;
 
@@ -1039,20 +1041,33 @@ vmis_predict_kernel(const IndexView ix, const PredictArgs a, const LaunchPlan pl
       if (!S.overflow && S.n_occ <= plan.occ_cap) {
         written = select_table(ix, a, S, X, reinterpret_cast<uint32_t*>(gran_nbr), c, stab, plan.tab_cap);
       } else {
-        // redo on this CTA's global table: big enough for every item of every neighbour, cleaned after use
-        Slot* gtab = ws.gtab + (size_t)blockIdx.x * ws.gtab_cap;
-        uint32_t* gocc = ws.gtab_occ + (size_t)blockIdx.x * (ws.gtab_cap / 2);
+        // redo on a table in HBM sized for THIS query (every item of every neighbour distinct): the CTA's own
+        // overflow table, or — a neighbourhood of very long sessions — the one huge table, taken under a lock.
+        // Either is all-empty between uses and cleaned through its occupied-slot list.
+        uint32_t need = 1024u;
+        while (need < 2u * total_items && need < 0x80000000u) need <<= 1;
+        const bool huge = need > ws.gtab_cap;                          // plan_launch sized ws.gtab_huge for the worst case
+        Slot* gtab = huge ? ws.huge : ws.gtab + (size_t)blockIdx.x * ws.gtab_cap;
+        uint32_t* gocc = huge ? ws.huge_occ : ws.gtab_occ + (size_t)blockIdx.x * (ws.gtab_cap / 2);
         __syncthreads();
-        if (tid == 0) { S.n_occ = 0; S.overflow = 0; S.round = 0; }
+        if (tid == 0) {
+          S.n_occ = 0; S.overflow = 0; S.round = 0;
+          if (huge) { while (atomicCAS(ws.counter + 2, 0u, 1u) != 0u) __nanosleep(500); __threadfence(); }
+        }
         __syncthreads();
-        if (flat) accumulate<true>(ix, S, nl, nn, G, last_idx, gtab, ws.gtab_cap - 1, false, 0u);
-        else accumulate<false>(ix, S, nl, nn, G, last_idx, gtab, ws.gtab_cap - 1, false, 0u);
+        if (flat) accumulate<true>(ix, S, nl, nn, G, last_idx, gtab, need - 1, false, 0u);
+        else accumulate<false>(ix, S, nl, nn, G, last_idx, gtab, need - 1, false, 0u);
         __syncthreads();
-        compact_slots<uint32_t>(S, par, gtab, ws.gtab_cap, gocc, ws.gtab_cap / 2);
+        compact_slots<uint32_t>(S, par, gtab, need, gocc, need / 2);
         __syncthreads();
         const uint32_t n_occ = S.n_occ;
         written = select_exact<false, uint32_t>(ix, a, S, X, c, gtab, gocc, n_occ);
         for (uint32_t e = tid; e < n_occ; e += kThreads) gtab[gocc[e]] = kEmptySlot;
+        if (huge) {
+          __threadfence();
+          __syncthreads();
+          if (tid == 0) atomicExch(ws.counter + 2, 0u);
+        }
       }
     }
     for (uint32_t i = written + tid; i < N; i += kThreads) {           // deterministic padding
@@ -1085,8 +1100,10 @@ uint32_t next_pow2(uint32_t x) { uint32_t p = 1; while (p < x) p <<= 1; return p
 
 }  // namespace
 
-int plan_launch(const IndexView& ix, uint32_t k, uint32_t m, int sm_count, LaunchPlan* plan) {
-  if (k > kMaxK || m > kMaxM) return VMIS_ERR_LIMIT;
+int plan_launch(const IndexView& ix, uint32_t k, uint32_t m, int sm_count, LaunchPlan* plan, std::string* why) {
+  auto refuse = [&](const std::string& msg) { if (why) *why = msg; return VMIS_ERR_LIMIT; };
+  if (k > kMaxK) return refuse("k = " + std::to_string(k) + " exceeds the kernel limit of " + std::to_string(kMaxK));
+  if (m > kMaxM) return refuse("m = " + std::to_string(m) + " exceeds the kernel limit of " + std::to_string(kMaxM));
   LaunchPlan p{};
   // one extra entry each: the merge steps read a sentinel behind both runs
   p.m_eff = (std::max(m, 1u) + 1u + 3u) & ~3u;
@@ -1110,37 +1127,55 @@ int plan_launch(const IndexView& ix, uint32_t k, uint32_t m, int sm_count, Launc
   p.gran_cap &= ~7u;
   const size_t r2 = size_t(p.tab_cap) * 8 + gran_bytes(p.gran_cap);
   const size_t total = fixed + nbr + std::max(std::max(r1, r2), size_t(kMaxSessionLen) * 8) + 16;
-  if (total > 227 * 1024) return VMIS_ERR_LIMIT;
+  if (total > 227 * 1024)
+    return refuse("k = " + std::to_string(k) + ", m = " + std::to_string(m) + " need " + std::to_string(total) +
+                  " bytes of shared memory per query (limit 232448): lower k or m");
   p.smem_bytes = (uint32_t)total;
   int per_sm = (int)std::min<size_t>(kCtasPerSm, (227 * 1024) / (total + 1024));
   if (const char* e = std::getenv("VMIS_CTAS_PER_SM")) per_sm = std::min(per_sm, std::max(1, std::atoi(e)));   // tuning knob
   if (per_sm < 1) per_sm = 1;
   p.grid = (uint32_t)(sm_count * per_sm);
+  // overflow score tables in HBM: every resident CTA owns a small one (up to 2^15 slots, enough for a neighbourhood
+  // of 16 k items); the rare query beyond that takes the single table sized for the worst case (k sessions of max_len
+  // items, all distinct) under a lock
   const uint64_t gt = 2ull * std::max(k, 1u) * std::max(ix.max_len, 1u);
-  if (gt > (1ull << 30)) return VMIS_ERR_LIMIT;
-  p.gtab_cap = next_pow2(std::max<uint32_t>((uint32_t)gt, 1024u));
+  const uint64_t worst = gt > (1ull << 31) ? 0 : next_pow2(std::max<uint32_t>((uint32_t)gt, 1024u));
+  p.gtab_cap = (uint32_t)std::min<uint64_t>(worst ? worst : (1u << 15), 1u << 15);
+  p.gtab_huge = worst > p.gtab_cap ? (uint32_t)worst : 0u;
+  const uint64_t bytes = 10ull * p.gtab_cap * p.grid + 10ull * p.gtab_huge;
+  if (worst == 0 || bytes > kMaxWorkspaceBytes)
+    return refuse("the longest indexed session has " + std::to_string(ix.max_len) + " items: k = " + std::to_string(k) +
+                  " neighbours of that length need an overflow score table of " + std::to_string(gt) + " slots (" +
+                  std::to_string((worst ? bytes : gt * 10ull) >> 20) + " MB, limit " + std::to_string(kMaxWorkspaceBytes >> 20) +
+                  " MB); prune long sessions when loading the index (max_session_len of vmis_index_from_avro_ex / "
+                  "vmis_index_from_parts_ex; the reference's CSV path prunes at the 99.5th length percentile, "
+                  "vmis_index.rs:67,452) or lower k");
   *plan = p;
   return VMIS_OK;
 }
 
 size_t workspace_bytes(const LaunchPlan& plan) {
-  return 256 + size_t(plan.grid) * plan.gtab_cap * (8 + 2);
+  return 256 + (size_t(plan.grid) * plan.gtab_cap + plan.gtab_huge) * (8 + 2);
 }
 
 Workspace carve_workspace(void* base, const LaunchPlan& plan) {
   Workspace ws{};
   unsigned char* b = static_cast<unsigned char*>(base);
+  const size_t n = size_t(plan.grid) * plan.gtab_cap;
   ws.counter = reinterpret_cast<uint32_t*>(b);
   ws.gtab = reinterpret_cast<unsigned long long*>(b + 256);
-  ws.gtab_occ = reinterpret_cast<uint32_t*>(b + 256 + size_t(plan.grid) * plan.gtab_cap * 8);
+  ws.huge = ws.gtab + n;
+  ws.gtab_occ = reinterpret_cast<uint32_t*>(b + 256 + (n + plan.gtab_huge) * 8);
+  ws.huge_occ = ws.gtab_occ + n / 2;
   ws.gtab_cap = plan.gtab_cap;
+  ws.gtab_huge = plan.gtab_huge;
   ws.grid = plan.grid;
   return ws;
 }
 
 cudaError_t init_workspace(const Workspace& ws, cudaStream_t stream) {
-  const size_t n = size_t(ws.grid) * ws.gtab_cap;
-  cudaError_t e = cudaMemsetAsync(ws.counter, 0, 2 * sizeof(uint32_t), stream);   // work counter + exit counter
+  const size_t n = size_t(ws.grid) * ws.gtab_cap + ws.gtab_huge;
+  cudaError_t e = cudaMemsetAsync(ws.counter, 0, 4 * sizeof(uint32_t), stream);   // work counter, exit counter, lock
   if (e != cudaSuccess) return e;
   return cudaMemsetAsync(ws.gtab, 0xFF, n * 8, stream);                            // all ones = empty slot
 }

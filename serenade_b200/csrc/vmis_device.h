@@ -3,6 +3,7 @@
 // boundary is include/vmis.h).
 #pragma once
 #include <cstdint>
+#include <string>
 #include <cuda_runtime.h>
 
 #include "../../include/vmis.h"
@@ -84,10 +85,13 @@ struct PredictArgs {
 // overflow score table per resident CTA.  Invariant: between launches every table
 // slot is {kEmpty, 0} (init_workspace() establishes it, the kernel restores it).
 struct Workspace {
-  uint32_t* counter;          // [0] work counter, [1] exit counter; zero between launches (the last CTA re-arms them)
+  uint32_t* counter;          // [0] work counter, [1] exit counter, [2] lock of the huge table; zero between launches
   unsigned long long* gtab;   // grid × gtab_cap score-table slots {key : 32 | value : 32}, all ones = empty
   uint32_t* gtab_occ;         // grid × gtab_cap / 2: occupied-slot lists
-  uint32_t gtab_cap;          // power of two >= 2 * k * max_len
+  unsigned long long* huge;   // ONE table of gtab_huge slots for the rare query that outgrows its CTA's table (taken
+  uint32_t* huge_occ;         // under the lock); its occupied-slot list
+  uint32_t gtab_cap;          // per-CTA overflow table: power of two, min(2 * k * max_len, 2^15) slots
+  uint32_t gtab_huge;         // 0, or the power of two >= 2 * k * max_len when that exceeds gtab_cap
   uint32_t grid;
 };
 
@@ -100,10 +104,11 @@ struct LaunchPlan {
   uint32_t m_eff;             // acc buffer capacity
   uint32_t list_cap;          // posting staging capacity
   uint32_t gtab_cap;
+  uint32_t gtab_huge;
 };
 
-// Computes launch geometry; returns VMIS_OK or VMIS_ERR_LIMIT.
-int plan_launch(const IndexView& ix, uint32_t k, uint32_t m, int sm_count, LaunchPlan* plan);
+// Computes launch geometry; returns VMIS_OK or VMIS_ERR_LIMIT (then *why names the limit that was hit and the remedy).
+int plan_launch(const IndexView& ix, uint32_t k, uint32_t m, int sm_count, LaunchPlan* plan, std::string* why);
 size_t workspace_bytes(const LaunchPlan& plan);
 // carve a raw device allocation of workspace_bytes() into a Workspace
 Workspace carve_workspace(void* base, const LaunchPlan& plan);

@@ -34,7 +34,7 @@ class _Stats(C.Structure):
 
 class _PrebuiltInfo(C.Structure):
     _fields_ = [(n, C.c_uint64) for n in ("item_files", "session_files", "item_records", "session_records",
-                                          "lists_reordered", "duplicate_postings")] + [("m_carry", C.c_uint32),
+                                          "lists_reordered", "duplicate_postings", "pruned_postings")] + [("m_carry", C.c_uint32),
                                                                                        ("prebuilt", C.c_uint32)]
 
 
@@ -65,6 +65,8 @@ def load_library():
         "vmis_index_synth": (vp, [u64, u64, u64, sz, sz, f64, i32, u32, u32]),
         "vmis_index_from_avro": (vp, [C.c_char_p, i32]),
         "vmis_index_from_avro_sharded": (vp, [C.c_char_p, i32, u32, u32]),
+        "vmis_index_from_avro_ex": (vp, [C.c_char_p, i32, u32, u32, sz]),
+        "vmis_index_from_parts_ex": (vp, [_u64p, _u64p, _u32p, _f64p, _u8p, sz, _u64p, _u64p, _u32p, sz, i32, u32, u32, sz]),
         "vmis_index_from_parts": (vp, [_u64p, _u64p, _u32p, _f64p, _u8p, sz, _u64p, _u64p, _u32p, sz, i32, u32, u32]),
         "vmis_index_prebuilt_info": (i32, [vp, C.POINTER(_PrebuiltInfo)]),
         "vmis_index_to_avro": (i32, [vp, C.c_char_p, C.c_char_p, u32]),
@@ -116,7 +118,7 @@ EXPORTED_SYMBOLS = ("vmis_index_from_csv", "vmis_index_from_csv_ex", "vmis_sessi
                     "vmis_sessions_free", "vmis_index_from_sessions", "vmis_index_from_sessions_attrs",
                     "vmis_index_from_sessions_sharded", "vmis_index_export_shard", "vmis_index_attach_shard",
                     "vmis_index_attach_shard_ptr", "vmis_index_shard_ptr", "vmis_index_from_device_sessions",
-                    "vmis_index_synth", "vmis_index_from_avro", "vmis_index_from_avro_sharded", "vmis_index_from_parts",
+                    "vmis_index_synth", "vmis_index_from_avro", "vmis_index_from_avro_sharded", "vmis_index_from_avro_ex", "vmis_index_from_parts", "vmis_index_from_parts_ex",
                     "vmis_index_prebuilt_info", "vmis_index_to_avro", "vmis_index_save", "vmis_index_load",
                     "vmis_index_set_attributes", "vmis_index_free", "vmis_index_stats", "vmis_predict_batch",
                     "vmis_predict_batch_device", "vmis_predict", "vmis_find_neighbors_batch", "vmis_items_for_session",
@@ -213,14 +215,14 @@ class VMISIndex:
                                       device, shard, n_shards))
 
     @classmethod
-    def new(cls, base_path, device=0, shard=0, n_shards=1):
+    def new(cls, base_path, device=0, shard=0, n_shards=1, max_session_len=0):
         """``VMISIndex::new(base_path)`` (vmis_index.rs:85): the production index from ``<base_path>/itemindex/*.avro``
-        and ``<base_path>/sessionindex/*.avro``."""
-        return cls(load_library().vmis_index_from_avro_sharded(os.fsencode(base_path), device, shard, n_shards))
+        and ``<base_path>/sessionindex/*.avro``.  max_session_len > 0 drops longer sessions from the posting lists."""
+        return cls(load_library().vmis_index_from_avro_ex(os.fsencode(base_path), device, shard, n_shards, max_session_len))
 
     @classmethod
     def from_parts(cls, item_ids, post_off, post_sessions, idf, attr, items, sess_off, sess_ts, device=0, shard=0,
-                   n_shards=1):
+                   n_shards=1, max_session_len=0):
         """The pre-computed index of ``VMISIndex::new`` from arrays in memory (posting lists, idf, attributes as given)."""
         L = load_library()
         item_ids = np.ascontiguousarray(item_ids, dtype=np.uint64)
@@ -231,11 +233,11 @@ class VMISIndex:
         items = np.ascontiguousarray(items, dtype=np.uint64)
         sess_off = np.ascontiguousarray(sess_off, dtype=np.uint64)
         sess_ts = np.ascontiguousarray(sess_ts, dtype=np.uint32)
-        return cls(L.vmis_index_from_parts(_p(item_ids, C.c_uint64), _p(post_off, C.c_uint64),
-                                           _p(post_sessions, C.c_uint32), _p(idf, C.c_double),
-                                           None if attr is None else _p(attr, C.c_uint8), len(item_ids),
-                                           _p(items, C.c_uint64), _p(sess_off, C.c_uint64), _p(sess_ts, C.c_uint32),
-                                           len(sess_ts), device, shard, n_shards))
+        return cls(L.vmis_index_from_parts_ex(_p(item_ids, C.c_uint64), _p(post_off, C.c_uint64),
+                                              _p(post_sessions, C.c_uint32), _p(idf, C.c_double),
+                                              None if attr is None else _p(attr, C.c_uint8), len(item_ids),
+                                              _p(items, C.c_uint64), _p(sess_off, C.c_uint64), _p(sess_ts, C.c_uint32),
+                                              len(sess_ts), device, shard, n_shards, max_session_len))
 
     def prebuilt_info(self):
         pi = _PrebuiltInfo()

@@ -139,3 +139,38 @@ def test_device_built_index_exports_and_reloads(sb, oracle, tmp_path):
     b = sb.predict_batch(back, q, 100, 300, 21)
     for x, y in zip(a, b):
         assert np.array_equal(x, y)
+
+
+def test_long_sessions_in_a_prebuilt_index(sb, oracle):
+    """the offline index keeps every session (the reference's production statistics name one of 9408
+    events).  Without a bound, a query whose worst-case score table (k x longest session) exceeds the workspace limit
+    is refused with a message that names the session length and the remedy; with max_session_len the long sessions
+    leave the posting lists (as prepare_hashmap does, vmis_index.rs:452) and the index answers like the oracle holding
+    the pruned lists."""
+    rng = np.random.default_rng(7)
+    items, off, ts = random_index_data(rng, 400, 60, max_len=8, id_scale=31)
+    # one giant session: 300 000 distinct items (58 of them shared with the small sessions)
+    giant = np.concatenate([np.unique(items)[:58], np.arange(10_000_000, 10_000_000 + 299_942, dtype=np.uint64)])
+    items = np.concatenate([items, np.sort(giant)])
+    off = np.concatenate([off, [off[-1] + len(giant)]]).astype(np.uint64)
+    ts = np.concatenate([ts, [5_000_000]]).astype(np.uint32)
+    src = oracle.OracleIndex.from_sessions(items, off, ts, 50, 400_000, 2.0)
+    parts = au.parts_from_oracle(src, items, off, ts)
+    args = (parts["item_ids"], parts["post_off"], parts["post_sessions"], parts["idf"], None, parts["items"], parts["off"],
+            parts["ts"])
+    full = sb.VMISIndex.from_parts(*args, device=0)
+    qs = _queries(rng, np.unique(items)[:58], 64)
+    with pytest.raises(sb.VmisError) as e:
+        sb.predict_batch(full, qs, 2000, 50, 21)
+    assert e.value.code == -4 and "300000 items" in str(e.value) and "max_session_len" in str(e.value)
+    _equal(sb, full, _oracle_from_parts(oracle, parts), qs, 20, 50, 21)      # a small k still fits: the giant is scored
+    pruned = sb.VMISIndex.from_parts(*args, device=0, max_session_len=8)
+    assert pruned.prebuilt_info()["pruned_postings"] == 300_000
+    keep = np.array([s != 400 for s in parts["post_sessions"]])
+    p2 = dict(parts)
+    cnt = np.add.reduceat(keep.astype(np.int64), parts["post_off"][:-1].astype(np.int64)) if len(keep) else np.zeros(0, np.int64)
+    cnt[np.diff(parts["post_off"].astype(np.int64)) == 0] = 0
+    p2["post_sessions"] = parts["post_sessions"][keep]
+    p2["post_off"] = np.concatenate([[0], np.cumsum(cnt)]).astype(np.uint64)
+    _equal(sb, pruned, _oracle_from_parts(oracle, p2), qs, 2000, 50, 21)
+    _equal(sb, pruned, _oracle_from_parts(oracle, p2), qs, 20, 50, 21)
