@@ -6,6 +6,7 @@
 #include "avro_reader.h"
 
 #include <algorithm>
+#include <cerrno>
 #include <atomic>
 #include <cmath>
 #include <cstdio>
@@ -151,14 +152,28 @@ bool read_sessions_from_csv(const std::string& path, Sessions* out, std::string*
         const size_t len = std::strlen(p);
         pos += len + 1;
         if (len == 0 || *p == '\r') continue;
+        // (usize, usize, f64) through csv + serde (:604-609): exactly three fields; the integers are digits with an
+        // optional '+' (no sign, no blanks, no overflow); the float is what Rust's f64::from_str takes.  Anything else
+        // is the reference's "Unable to parse input!" → the row is skipped.
+        auto uint_token = [](const char* q) { return (*q >= '0' && *q <= '9') || (*q == '+' && q[1] >= '0' && q[1] <= '9'); };
         char* e = nullptr;
+        if (!uint_token(p)) { ++bad_rows[t]; continue; }
+        errno = 0;
         const unsigned long long sid = std::strtoull(p, &e, 10);
-        if (e == p || *e != '\t') { ++bad_rows[t]; continue; }
-        p = e + 1; const unsigned long long iid = std::strtoull(p, &e, 10);
-        if (e == p || *e != '\t') { ++bad_rows[t]; continue; }
-        p = e + 1; const double tm = std::strtod(p, &e);
-        if (e == p) { ++bad_rows[t]; continue; }
-        rows.push_back(Row{sid, iid, (uint64_t)std::llround(tm)});                 // (usize, usize, f64.round()) :607-609
+        if (errno == ERANGE || *e != '\t') { ++bad_rows[t]; continue; }
+        p = e + 1;
+        if (!uint_token(p)) { ++bad_rows[t]; continue; }
+        errno = 0;
+        const unsigned long long iid = std::strtoull(p, &e, 10);
+        if (errno == ERANGE || *e != '\t') { ++bad_rows[t]; continue; }
+        p = e + 1;
+        if (*p == ' ' || *p == '\t' || *p == '\0' || *p == '\r' || (p[0] == '0' && (p[1] == 'x' || p[1] == 'X'))) { ++bad_rows[t]; continue; }
+        const double tm = std::strtod(p, &e);
+        if (e == p || !(*e == '\0' || (*e == '\r' && e[1] == '\0'))) { ++bad_rows[t]; continue; }   // a 4th field or trailing junk
+        // `raw.2.round() as usize` (:607-609): Rust's float → integer cast saturates (NaN and negatives give 0)
+        const double r = std::round(tm);
+        const uint64_t tsec = !(r > 0.0) ? 0ull : r >= 18446744073709551615.0 ? ~0ull : (uint64_t)r;
+        rows.push_back(Row{sid, iid, tsec});
       }
     };
     for (size_t t = 1; t < nt; ++t) th.emplace_back(parse, t);
@@ -219,6 +234,12 @@ bool read_sessions_from_csv(const std::string& path, Sessions* out, std::string*
       close_session();
       cur.clear(); cur.push_back(rows[i].item); max_ts = rows[i].time;
     }
+  }
+  if (out->ts.empty()) {
+    // e.g. a single data row: the last-row handling drops it and nothing is left.  The reference goes on to panic
+    // (empty percentile digest, vmis_index.rs:689-716); an empty index is never what the caller meant.
+    *err = "no training session survives read_from_file in " + path + " (the last sorted row is always dropped, vmis_index.rs:666-686)";
+    return false;
   }
   return true;
 }

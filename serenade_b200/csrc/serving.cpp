@@ -22,6 +22,7 @@
 #include <vector>
 
 #include "../../include/vmis.h"
+#include "vmis_host.h"
 
 namespace {
 
@@ -129,7 +130,13 @@ extern "C" {
 vmis_server_t* vmis_server_create(const vmis_index_t* index, uint32_t k, uint32_t m, uint32_t how_many,
                                   uint32_t max_items_in_session, int enable_business_logic, uint32_t max_batch,
                                   uint32_t max_wait_us, uint64_t session_ttl_secs, uint64_t max_session_idle_secs) {
-  if (!index || max_items_in_session == 0) return nullptr;
+  if (!index || max_items_in_session == 0) { vmis::set_last_error(VMIS_ERR_ARG, "vmis_server_create: NULL index or max_items_in_session == 0"); return nullptr; }
+  // a window longer than the kernel takes would make every request of a long visit fail (and, before requests were
+  // validated one by one, its batch mates too): refuse the configuration instead
+  if (max_items_in_session > VMIS_MAX_SESSION_LEN) {
+    vmis::set_last_error(VMIS_ERR_LIMIT, "max_items_in_session exceeds VMIS_MAX_SESSION_LEN (128)");
+    return nullptr;
+  }
   vmis_server* s = new vmis_server();
   s->batcher = vmis_batcher_create(index, k, m, how_many, enable_business_logic, max_batch ? max_batch : 4096, max_wait_us);
   if (!s->batcher) { delete s; return nullptr; }

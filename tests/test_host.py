@@ -285,3 +285,43 @@ def test_parallel_tsv_reader_matches_the_serial_restatement(sb, oracle, tmp_path
         np.testing.assert_array_equal(items[off[s]:off[s + 1]], oix.items_for_session(s))
         assert ts[s] == oix.session_ts(s)
     assert int(off[-1]) == sum(len(oix.items_for_session(s)) for s in range(len(ts)))
+
+
+def test_tsv_parser_is_as_strict_as_csv_serde(sb, oracle, tmp_path):
+    """rows the reference's csv + serde (usize, usize, f64) parse rejects are skipped here too — signs,
+    blanks, a 4th column, overflow — and the float → usize cast saturates like Rust's `as` (vmis_index.rs:604-609)."""
+    good = ["1\t10\t100.0", "1\t11\t101.4", "2\t10\t200", "2\t12\t201", "3\t13\t300", "3\t14\t3e2", "4\t15\t400", "4\t16\t401"]
+    bad = ["-5\t10\t100", " 6\t10\t100", "7\t-1\t100", "8\t10\t100\t9", "9\t10\tabc", "99999999999999999999999\t1\t1",
+           "10\t10\t 5", "11\t10", "12\t10\t0x10"]
+    p = tmp_path / "t.txt"
+    rows = []
+    for i, g in enumerate(good):
+        rows.append(g)
+        if i < len(bad):
+            rows.append(bad[i])
+    rows += bad[len(good):]
+    p.write_text("SessionId\tItemId\tTime\n" + "\n".join(rows) + "\n")
+    items, off, ts = sb.read_sessions_csv(str(p))
+    q = tmp_path / "clean.txt"
+    q.write_text("SessionId\tItemId\tTime\n" + "\n".join(good) + "\n")
+    items2, off2, ts2 = sb.read_sessions_csv(str(q))
+    assert np.array_equal(items, items2) and np.array_equal(off, off2) and np.array_equal(ts, ts2)
+    assert len(ts) == 4 and list(ts[:3]) == [101, 201, 300]          # "+"-less plain rows; 101.4 rounds to 101
+    # saturating casts: negative and NaN times become 0
+    r = tmp_path / "neg.txt"
+    r.write_text("SessionId\tItemId\tTime\n1\t10\t-7.5\n1\t11\tNaN\n2\t12\t5\n2\t13\t6\n")
+    _, _, ts3 = sb.read_sessions_csv(str(r))
+    assert list(ts3) == [0, 5]           # session 2 keeps item 12 only: the last sorted row is dropped (:666-686)
+    # a file whose only data row is swallowed by the last-row quirk is an error, not an empty index
+    one = tmp_path / "one.txt"
+    one.write_text("SessionId\tItemId\tTime\n1\t10\t5\n")
+    with pytest.raises(sb.VmisError) as e:
+        sb.read_sessions_csv(str(one))
+    assert e.value.code == -2
+
+
+def test_server_refuses_windows_longer_than_the_kernel_limit(sb):
+    items, off, ts = random_index_data(np.random.default_rng(5), 50, 10)
+    hix = sb.VMISIndex.from_sessions(items, off, ts, 10, 8, 1.0, device=sb.DEVICE_NONE)
+    with pytest.raises(sb.VmisError):
+        sb.Server(hix, 5, 10, 5, max_items_in_session=129)
