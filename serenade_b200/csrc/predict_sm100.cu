@@ -209,6 +209,7 @@ struct SmemLayout {
   alignas(16) uint32_t top4[kWarps][4];   // phase 3: the four best thread candidates of every warp
   uint32_t qcount;                   // phase 3: entries in the block-wide candidate queue
   unsigned long long bar[2];         // mbarriers of the two posting-list staging buffers (TMA bulk copies)
+  unsigned long long stage[kWarps][32];   // phase 2b: per-warp staging of the items whose first probe collided
 };
 // Scratch that aliases the neighbour arrays (dead or not yet written when it is live): the per-warp numerator
 // histogram of phase 1b and the cross-warp candidate buffers of phase 3.
@@ -293,43 +294,41 @@ __device__ __forceinline__ void insert_granule(SmemLayout& S, const uint4 it, in
   if (v2 && k2 == it.z) atomicAdd(reinterpret_cast<int*>(&tab[h2]), w);
   if (v3 && k3 == it.w) atomicAdd(reinterpret_cast<int*>(&tab[h3]), w);
   nclaim += (uint32_t)(v0 && k0 == kEmpty) + (uint32_t)(v1 && k1 == kEmpty) + (uint32_t)(v2 && k2 == kEmpty) + (uint32_t)(v3 && k3 == kEmpty);
-  const bool c0 = v0 && k0 != kEmpty && k0 != it.x, c1 = v1 && k1 != kEmpty && k1 != it.y;
-  const bool c2 = v2 && k2 != kEmpty && k2 != it.z, c3 = v3 && k3 != kEmpty && k3 != it.w;
-  uint32_t pend = 0;
-  if (__any_sync(kFull, c0 || c1 || c2 || c3)) {
-    // stage B: the second probes of the collided items, again all in flight before any result is looked at
-    const uint32_t g0 = (h0 + hash_stride(it.x)) & mask, g1 = (h1 + hash_stride(it.y)) & mask;
-    const uint32_t g2 = (h2 + hash_stride(it.z)) & mask, g3 = (h3 + hash_stride(it.w)) & mask;
-    Slot p0 = 0, p1 = 0, p2 = 0, p3 = 0;
-    if (c0) p0 = atomicCAS(&tab[g0], kEmptySlot, make_slot(it.x, w));
-    if (c1) p1 = atomicCAS(&tab[g1], kEmptySlot, make_slot(it.y, w));
-    if (c2) p2 = atomicCAS(&tab[g2], kEmptySlot, make_slot(it.z, w));
-    if (c3) p3 = atomicCAS(&tab[g3], kEmptySlot, make_slot(it.w, w));
-    const uint32_t q0 = slot_key(p0), q1 = slot_key(p1), q2 = slot_key(p2), q3 = slot_key(p3);
-    if (c0 && q0 == it.x) atomicAdd(reinterpret_cast<int*>(&tab[g0]), w);
-    if (c1 && q1 == it.y) atomicAdd(reinterpret_cast<int*>(&tab[g1]), w);
-    if (c2 && q2 == it.z) atomicAdd(reinterpret_cast<int*>(&tab[g2]), w);
-    if (c3 && q3 == it.w) atomicAdd(reinterpret_cast<int*>(&tab[g3]), w);
-    nclaim += (uint32_t)(c0 && q0 == kEmpty) + (uint32_t)(c1 && q1 == kEmpty) + (uint32_t)(c2 && q2 == kEmpty) + (uint32_t)(c3 && q3 == kEmpty);
-    pend = (c0 && q0 != kEmpty && q0 != it.x ? 1u : 0u) | (c1 && q1 != kEmpty && q1 != it.y ? 2u : 0u) |
-           (c2 && q2 != kEmpty && q2 != it.z ? 4u : 0u) | (c3 && q3 != kEmpty && q3 != it.w ? 8u : 0u);
-  }
-  // the few items that collided twice: one at a time, from the third probe position on
-  while (__any_sync(kFull, pend != 0u)) {
-    if (pend != 0u) {
+  uint32_t pend = (v0 && k0 != kEmpty && k0 != it.x ? 1u : 0u) | (v1 && k1 != kEmpty && k1 != it.y ? 2u : 0u) |
+                  (v2 && k2 != kEmpty && k2 != it.z ? 4u : 0u) | (v3 && k3 != kEmpty && k3 != it.w ? 8u : 0u);
+  // stage B: the collided items (about one in five) are dealt out again, ONE per lane, through a 32-entry staging row
+  // of the warp, and every lane walks the rest of its item's probe sequence — a couple of trips with most lanes busy
+  // instead of four mostly idle slots per lane
+  const uint32_t lane = threadIdx.x & 31u;
+  unsigned long long* stage = S.stage[threadIdx.x >> 5];
+  for (;;) {
+    const int cnt = __popc(pend);
+    if (!__any_sync(kFull, cnt != 0)) break;
+    const int incl = warp_incl_scan(cnt, (int)lane);
+    const uint32_t total = (uint32_t)__shfl_sync(kFull, incl, 31);
+    uint32_t pos = (uint32_t)(incl - cnt);
+    while (pend != 0u && pos < 32u) {
       const uint32_t item = (pend & 1u) ? it.x : (pend & 2u) ? it.y : (pend & 4u) ? it.z : it.w;
       pend &= pend - 1u;
+      stage[pos++] = make_slot(item, w);
+    }
+    __syncwarp();
+    if (lane < min(total, 32u)) {
+      const Slot e = stage[lane];
+      const uint32_t item = slot_key(e);
+      const int32_t wi = slot_val(e);
       const uint32_t stride = hash_stride(item);
-      uint32_t h = hash_slot(item) + stride;
+      uint32_t h = hash_slot(item);
       uint32_t tries = mask;                             // every other slot once
       for (;;) {
         h = (h + stride) & mask;
-        const uint32_t ok = slot_key(atomicCAS(&tab[h], kEmptySlot, make_slot(item, w)));
+        const uint32_t ok = slot_key(atomicCAS(&tab[h], kEmptySlot, e));
         if (ok == kEmpty) { ++nclaim; break; }
-        if (ok == item) { atomicAdd(reinterpret_cast<int*>(&tab[h]), w); break; }
+        if (ok == item) { atomicAdd(reinterpret_cast<int*>(&tab[h]), wi); break; }
         if (--tries == 0u) { S.overflow = 1u; break; }   // unreachable while the table has a free slot
       }
     }
+    __syncwarp();
   }
 }
 
@@ -578,20 +577,22 @@ __device__ __forceinline__ uint32_t select_table(const IndexView& ix, const Pred
 #pragma unroll
       for (int j = 0; j < 16; ++j) keep |= (cc[j] >= thr ? 1u : 0u) << j;
       if (keep != 0u) {                                                   // a handful of lanes per query
-        const uint32_t first = atomicAdd(&S.qcount, (uint32_t)__popc(keep));
-        uint32_t pos = first;
-#pragma unroll
-        for (int j = 0; j < 16; ++j) {
-          if ((keep >> j) & 1u) { if (pos < kSelQ) queue[pos] = cc[j]; ++pos; }
-        }
-        // the first 32 entries of the queue are rescored exactly right here, by the thread that queued them (all
-        // warps in parallel, off the serial tail): f64 g(idf) * A / (10 u), mod.rs:145-152
-        for (uint32_t p = first; p < pos && p < 32u; ++p) {
-          const Slot sl = tab[queue[p] & kIdxMask];
-          asm volatile("prefetch.global.L2 [%0];" ::"l"(ix.item_key + slot_key(sl)));   // read by the tail
-          const Elem e = exact_elem(ix, a, c, slot_key(sl), slot_val(sl), denom);
-          X.ex.s[p] = e.s; X.ex.id[p] = e.id;
-        }
+        uint32_t pos = atomicAdd(&S.qcount, (uint32_t)__popc(keep));
+        // The queue holds slot numbers.  Its first 32 entries are rescored exactly right here, by the thread that
+        // queued them (all warps in parallel, off the serial tail): f64 g(idf) * A / (10 u), mod.rs:145-152
+        do {
+          const uint32_t j = (uint32_t)__ffs((int)keep) - 1u;
+          keep &= keep - 1u;
+          const uint32_t slot = 2u * ((ps * 8u + (j >> 1)) * kThreads + (uint32_t)tid) + (j & 1u);
+          if (pos < kSelQ) queue[pos] = slot;
+          if (pos < 32u) {
+            const Slot sl = tab[slot];
+            asm volatile("prefetch.global.L2 [%0];" ::"l"(ix.item_key + slot_key(sl)));   // read by the tail
+            const Elem e = exact_elem(ix, a, c, slot_key(sl), slot_val(sl), denom);
+            X.ex.s[pos] = e.s; X.ex.id[pos] = e.id;
+          }
+          ++pos;
+        } while (keep != 0u);
       }
     }
     VMIS_CLK(S);
@@ -626,8 +627,11 @@ __device__ __forceinline__ uint32_t select_table(const IndexView& ix, const Pred
       if (ok) {
         // cut to the 32 best coarse keys; the cut is proven if the last one is more than a unit below the N-th
         uint32_t best = 0;
-        for (uint32_t b = 0; b < n; b += 32u)
-          best = u32_merge_top(best, u32_sort_desc(b + lane < n ? queue[b + lane] : 0u, lane), lane);
+        for (uint32_t b = 0; b < n; b += 32u) {
+          uint32_t key = 0u;
+          if (b + lane < n) { const uint32_t slot = queue[b + lane]; const Slot sl = tab[slot]; key = coarse(slot, slot_key(sl), (uint32_t)slot_val(sl)); }
+          best = u32_merge_top(best, u32_sort_desc(key, lane), lane);
+        }
         ok = (__shfl_sync(kFull, best, 31) >> kIdxBits) + 1u < (__shfl_sync(kFull, best, (int)N - 1) >> kIdxBits);
         if (ok) {
           take = N;
