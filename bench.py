@@ -46,6 +46,8 @@ WORKLOADS = {
 }
 DEVICE_BUILT = {"synthetic-582M-6.5M", "synthetic-2.3B-6.5M"}
 K, M, HOW_MANY, MAX_ITEMS, IDF_W, MAX_LEN = 288, 1502, 21, 4, 2.0, 34
+if os.environ.get("VMIS_BENCH_KM"):      # tuning experiments only (never a reported number): k,m override
+    K, M = (int(x) for x in os.environ["VMIS_BENCH_KM"].split(","))
 METRIC = "predict_next queries/sec @ k=288,m=1502"
 
 

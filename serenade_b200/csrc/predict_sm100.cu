@@ -42,7 +42,10 @@ namespace {
 
 constexpr unsigned kFull = 0xFFFFFFFFu;
 constexpr unsigned long long kMaxWorkspaceBytes = 8ull << 30;   // overflow tables of one call context
-constexpr int kVT = 8;                       // merge-path items per thread per tile
+#ifndef VMIS_VT
+#define VMIS_VT 6
+#endif
+constexpr int kVT = VMIS_VT;                 // merge-path items per thread per tile (A/B on B200: 4: 24.96, 5: 25.1, 6: 26.0, 7: 25.8, 8: 24.2, 9: 25.6, 11: 24.6 M qps — 8 is a bank-conflict pothole)
 constexpr int kTile = kThreads * kVT;
 
 struct Elem {          // top-n candidate: order-preserving score bits + dense item idx
@@ -569,8 +572,22 @@ __device__ __forceinline__ uint32_t select_table(const IndexView& ix, const Pred
         VMIS_CLK(S);
         __syncthreads();
         VMIS_CLK(S);
+#ifdef VMIS_BOUND_BY_RANK
+        // the N-th largest of the (up to 32) published keys by counting: every lane owns one key and counts the keys
+        // above it (broadcast reads, no shuffle chain); keys are unique, so exactly one lane has N - 1 above it
+        const uint32_t mine32 = (lane >> 2) < kWarps ? S.top4[lane >> 2][lane & 3] : 0u;
+        uint32_t above = 0;
+#pragma unroll
+        for (int w = 0; w < kWarps; ++w) {
+          const uint4 t = *reinterpret_cast<const uint4*>(S.top4[w]);
+          above += (t.x > mine32) + (t.y > mine32) + (t.z > mine32) + (t.w > mine32);
+        }
+        const uint32_t hit = __ballot_sync(kFull, mine32 != 0u && above == N - 1u);
+        const uint32_t bound = hit ? __shfl_sync(kFull, mine32, __ffs((int)hit) - 1) >> kIdxBits : 0u;   // 0: fewer than N candidates
+#else
         const uint32_t s32 = u32_sort_desc((lane >> 2) < kWarps ? S.top4[lane >> 2][lane & 3] : 0u, lane);
         const uint32_t bound = __shfl_sync(kFull, s32, (int)N - 1) >> kIdxBits;   // 0: fewer than N candidates so far
+#endif
         thr = bound > 1u ? (bound - 1u) << kIdxBits : 1u;
       }
       uint32_t keep = 0;
@@ -1116,6 +1133,9 @@ int plan_launch(const IndexView& ix, uint32_t k, uint32_t m, int sm_count, Launc
   // fills it (insert_granule relies on a free slot being reachable)
   const uint32_t tab = next_pow2(std::max(k, 1u) * 12u);
   p.tab_cap = std::min(std::max(tab, 4096u), 8192u);
+#ifdef VMIS_EXPERIMENT_TAB
+  p.tab_cap = VMIS_EXPERIMENT_TAB;   // occupancy experiments only: breaks the guard invariant below
+#endif
   p.occ_cap = p.tab_cap / 2 + p.tab_cap / 8;                        // 62.5 % of the slots
   const size_t fixed = (sizeof(SmemLayout) + 15) & ~size_t(15);
   const size_t nbr = nbr_bytes(k);
