@@ -308,7 +308,13 @@ int host_batch(const vmis_index* cix, const uint64_t* q_items, const uint32_t* q
   // The batch is cut into chunks that flow through a small ring of call contexts (own stream, staging buffers and
   // kernel workspace each): the H2D copy of chunk i+1 and the D2H copy of chunk i-1 overlap the kernel of chunk i.
   // With a caller-provided stream everything is enqueued there, in order.
-  constexpr uint32_t kChunk = 1u << 17;
+  // chunk of the pipeline (tuning knob VMIS_CHUNK_LOG2, default 2^17): smaller chunks shorten the fill / drain of the
+  // copy-kernel-copy pipeline, larger ones amortise the launches
+  static const uint32_t kChunk = [] {
+    const char* e = std::getenv("VMIS_CHUNK_LOG2");
+    const int l = e ? std::atoi(e) : 17;
+    return 1u << (l < 10 ? 10 : l > 20 ? 20 : l);
+  }();
   constexpr size_t kPipe = 3;
   const uint32_t n_chunks = (n_q + kChunk - 1) / kChunk;
   const size_t n_ctx = stream_ ? 1 : std::min<size_t>(kPipe, n_chunks);

@@ -219,7 +219,7 @@ struct SmemLayout {
 union Scratch {
   uint32_t hist[kWarps][32];
   struct { uint64_t s[kWarps * 32]; uint32_t id[kWarps * 32]; } top;      // exact path: per-warp top-32 lists
-  struct { uint64_t s[32]; uint32_t id[32]; } ex;                         // phase 3: exact elements of the first 32 queue entries
+  struct { uint64_t s[32]; uint64_t ext[32]; uint32_t id[32]; } ex;       // phase 3: exact elements (+ external ids) of the first 32 queue entries
 };
 constexpr uint32_t kSelQ = 1024;     // block-wide queue of top-n candidates (phase 3); more: exact scan
 
@@ -604,7 +604,11 @@ __device__ __forceinline__ uint32_t select_table(const IndexView& ix, const Pred
           if (pos < kSelQ) queue[pos] = slot;
           if (pos < 32u) {
             const Slot sl = tab[slot];
+#ifdef VMIS_EXT_AT_TAIL
             asm volatile("prefetch.global.L2 [%0];" ::"l"(ix.item_key + slot_key(sl)));   // read by the tail
+#else
+            X.ex.ext[pos] = ix.item_key[slot_key(sl)];                                     // the tail only reads shared memory
+#endif
             const Elem e = exact_elem(ix, a, c, slot_key(sl), slot_val(sl), denom);
             X.ex.s[pos] = e.s; X.ex.id[pos] = e.id;
           }
@@ -633,7 +637,11 @@ __device__ __forceinline__ uint32_t select_table(const IndexView& ix, const Pred
       rank += __shfl_xor_sync(kFull, rank, 2);
       rank += __shfl_xor_sync(kFull, rank, 4);
       if (((uint32_t)lane & 7u) == 0u && cnd < n && rank < N) {
+#ifdef VMIS_EXT_AT_TAIL
         a.out_ids[(size_t)q * N + rank] = ix.item_key[my.id];
+#else
+        a.out_ids[(size_t)q * N + rank] = X.ex.ext[cnd];
+#endif
         a.out_scores[(size_t)q * N + rank] = bits_score(my.s);
       }
       return min(n, N);
@@ -699,6 +707,21 @@ __device__ __forceinline__ void phase0_next(const IndexView& ix, const PredictAr
     S.d_idx[pos] = my_idx; S.d_pos[pos] = (uint8_t)lane;
   }
   if (lane == 0) { nx.nd = (uint32_t)__popc(known); nx.u = (uint32_t)__popc(uniq); nx.L = L; nx.ok = 1u; }
+#ifndef VMIS_NO_LIST_PREFETCH
+  // pull the heads of the next query's posting lists towards L2 while this query is still inserting: phase 1 then
+  // starts on warm lines instead of two dependent HBM round trips (post_ref, then the list).  Local shards only.
+  if (ix.n_shards == 1) {
+    uint2 ref = make_uint2(0u, 0u);
+    if (my_idx != kEmpty) ref = ix.post_ref[my_idx];
+    for (uint32_t src = known; src != 0u; src &= src - 1u) {
+      const int from = __ffs((int)src) - 1;
+      const uint32_t off4 = __shfl_sync(kFull, ref.x, from), len = __shfl_sync(kFull, ref.y, from);
+      const uint32_t lines = (min(len, a.m) * 4u + 127u) >> 7;                    // 128-byte lines of the list's first m entries
+      const unsigned char* base = reinterpret_cast<const unsigned char*>(ix.post_shard[0] + (size_t)off4 * 4);
+      for (uint32_t l = lane; l < lines; l += 32u) prefetch_l2(base + (size_t)l * 128u);
+    }
+  }
+#endif
 }
 
 __global__ void __launch_bounds__(kThreads, kCtasPerSm)
@@ -887,7 +910,13 @@ vmis_predict_kernel(const IndexView ix, const PredictArgs a, const LaunchPlan pl
           }
         } else {
           // v* = max v with count(num >= v) >= K  (numerators are >= 1)
+#ifdef VMIS_TOPK_EVEN
           const uint32_t E = (na + kThreads - 1) / kThreads;     // contiguous chunk per thread keeps recency order
+#else
+          // contiguous chunk per thread keeps recency order; an ODD chunk length makes the 64-bit reads of a warp
+          // (stride 2 E words) conflict free
+          const uint32_t E = ((na + kThreads - 1) / kThreads) | 1u;
+#endif
           const uint32_t e0 = min((uint32_t)tid * E, na), e1 = min(e0 + E, na);
           const uint32_t vmax = L * (L + 1) / 2;
           uint32_t vstar, tot_g;
@@ -991,6 +1020,9 @@ vmis_predict_kernel(const IndexView ix, const PredictArgs a, const LaunchPlan pl
 
     VMIS_CLK(S);
     // ------------------------------------------------------------------ phase 2a: neighbour directory
+    // the first neighbour's item list ref is requested before the table is cleared: the clear hides its latency
+    uint2 r_first = make_uint2(0u, 0u);
+    if ((uint32_t)tid < nn) r_first = ix.sess_ref[nbr_sid[tid]];
     {
       // all ones = empty; the capacity is a multiple of 4096: 16-byte stores
       uint4* t4 = reinterpret_cast<uint4*>(stab);
@@ -1001,7 +1033,7 @@ vmis_predict_kernel(const IndexView ix, const PredictArgs a, const LaunchPlan pl
     // neighbours tid, tid + 256, ...: item list refs, weights, granule counts (the order of the neighbours is free)
     uint32_t my_g = 0, my_len = 0;
     for (uint32_t i = tid; i < nn; i += kThreads) {
-      const uint2 r = ix.sess_ref[nbr_sid[i]];
+      const uint2 r = i == (uint32_t)tid ? r_first : ix.sess_ref[nbr_sid[i]];
       const uint32_t* items = ix.sess_items + (size_t)r.x * 4;
       prefetch_l2(items);                                           // the inserts read this list next
       if (r.y > 4u) prefetch_l2(items + (r.y - 1u));
