@@ -433,8 +433,8 @@ def b200_arm(args, rank, world, local_rank):
                 "algorithmic_bytes_per_query": timed_bytes / (S * B)}
 
     e2e = run.time_e2e(gix, batches, B, W, S)
-    e2e.update({"launches_per_step": (B + (1 << 17) - 1) >> 17,
-                "note": "vmis_predict_batch pipelines the batch in chunks of 2^17 sessions over 3 streams"})
+    e2e.update({"launches_per_step": (B + (1 << 15) - 1) >> 15,
+                "note": "vmis_predict_batch pipelines the batch in chunks of 2^15 sessions over 3 streams"})
     if world > 1:
         per_rank = [None] * world
         dist.all_gather_object(per_rank, {"rank": rank, "e2e_qps": e2e["rank_value"], "numa": numa})

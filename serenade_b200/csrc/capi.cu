@@ -31,9 +31,6 @@ int fail(int code, const char* fmt, ...) {
   g_err_code = code;
   return code;
 }
-// every successful public call that can fail clears the code, so `vmis_last_error_code() != 0` means "the last call
-// on this thread failed" (the code used to stick)
-inline int ok() { g_err_code = 0; return VMIS_OK; }
 #define CU_TRY(expr)                                                                     \
   do {                                                                                   \
     cudaError_t e__ = (expr);                                                            \
@@ -308,11 +305,11 @@ int host_batch(const vmis_index* cix, const uint64_t* q_items, const uint32_t* q
   // The batch is cut into chunks that flow through a small ring of call contexts (own stream, staging buffers and
   // kernel workspace each): the H2D copy of chunk i+1 and the D2H copy of chunk i-1 overlap the kernel of chunk i.
   // With a caller-provided stream everything is enqueued there, in order.
-  // chunk of the pipeline (tuning knob VMIS_CHUNK_LOG2, default 2^17): smaller chunks shorten the fill / drain of the
+  // chunk of the pipeline (tuning knob VMIS_CHUNK_LOG2, default 2^15; same-box e2e at 2^17 / 2^16 / 2^15: 24.33 / 24.54 / 24.65 M qps): smaller chunks shorten the fill / drain of the
   // copy-kernel-copy pipeline, larger ones amortise the launches
   static const uint32_t kChunk = [] {
     const char* e = std::getenv("VMIS_CHUNK_LOG2");
-    const int l = e ? std::atoi(e) : 17;
+    const int l = e ? std::atoi(e) : 15;
     return 1u << (l < 10 ? 10 : l > 20 ? 20 : l);
   }();
   constexpr size_t kPipe = 3;

@@ -183,6 +183,11 @@ __device__ __forceinline__ void bulk_load(void* dst_smem, const void* src_gmem, 
                    smem_u32(dst_smem)), "l"(src_gmem), "r"(bytes), "r"(smem_u32(bar)) : "memory");
 }
 __device__ __forceinline__ void prefetch_l2(const void* p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
+#ifdef VMIS_NO_PF_SESSREF
+#define PF_SESSREF(p) do {} while (0)
+#else
+#define PF_SESSREF(p) prefetch_l2(p)
+#endif
 __device__ __forceinline__ void fence_async_proxy() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 
 #ifdef VMIS_PHASE_CLOCKS
@@ -219,7 +224,7 @@ struct SmemLayout {
 union Scratch {
   uint32_t hist[kWarps][32];
   struct { uint64_t s[kWarps * 32]; uint32_t id[kWarps * 32]; } top;      // exact path: per-warp top-32 lists
-  struct { uint64_t s[32]; uint64_t ext[32]; uint32_t id[32]; } ex;       // phase 3: exact elements (+ external ids) of the first 32 queue entries
+  struct { uint64_t s[32]; uint32_t id[32]; } ex;                         // phase 3: exact elements of the first 32 queue entries
 };
 constexpr uint32_t kSelQ = 1024;     // block-wide queue of top-n candidates (phase 3); more: exact scan
 
@@ -527,6 +532,7 @@ __device__ __forceinline__ uint32_t select_exact(const IndexView& ix, const Pred
 //   4. warp 0: up to 32 survivors are rescored exactly (f64 g(idf) * A / (10 u)) and sorted once with the 96-bit
 //      network; more than 32 are first cut to the 32 best coarse keys, with the margin test proving that cut; if it
 //      cannot (heavy score ties) or the queue overflowed, select_exact() scans the table.
+template <bool kBiz>     // business rules on / off: compiled twice, so the plain call carries no trace of the filter
 __device__ __forceinline__ uint32_t select_table(const IndexView& ix, const PredictArgs& a, SmemLayout& S, Scratch& X,
                                                  uint32_t* queue, const QueryCtx& c, const Slot* tab, uint32_t tab_cap) {
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -541,7 +547,7 @@ __device__ __forceinline__ uint32_t select_table(const IndexView& ix, const Pred
       bool valid = key != kEmpty;
       float g = 0.0f;
       if (valid) g = __ldg(ix.g32 + key);                                  // mod.rs:145-152
-      if (a.biz) { if (valid && !passes_business_rules(c.cur_attr, ix.attr[key])) valid = false; }
+      if (kBiz) { if (valid && !passes_business_rules(c.cur_attr, ix.attr[key])) valid = false; }
       const uint32_t fb = __float_as_uint((float)(int32_t)A * g * rdenom);
       const uint32_t mono = fb ^ ((uint32_t)((int32_t)fb >> 31) | 0x80000000u);
       return valid ? ((mono & ~kIdxMask) | slot) : 0u;
@@ -604,11 +610,7 @@ __device__ __forceinline__ uint32_t select_table(const IndexView& ix, const Pred
           if (pos < kSelQ) queue[pos] = slot;
           if (pos < 32u) {
             const Slot sl = tab[slot];
-#ifdef VMIS_EXT_AT_TAIL
             asm volatile("prefetch.global.L2 [%0];" ::"l"(ix.item_key + slot_key(sl)));   // read by the tail
-#else
-            X.ex.ext[pos] = ix.item_key[slot_key(sl)];                                     // the tail only reads shared memory
-#endif
             const Elem e = exact_elem(ix, a, c, slot_key(sl), slot_val(sl), denom);
             X.ex.s[pos] = e.s; X.ex.id[pos] = e.id;
           }
@@ -637,11 +639,7 @@ __device__ __forceinline__ uint32_t select_table(const IndexView& ix, const Pred
       rank += __shfl_xor_sync(kFull, rank, 2);
       rank += __shfl_xor_sync(kFull, rank, 4);
       if (((uint32_t)lane & 7u) == 0u && cnd < n && rank < N) {
-#ifdef VMIS_EXT_AT_TAIL
         a.out_ids[(size_t)q * N + rank] = ix.item_key[my.id];
-#else
-        a.out_ids[(size_t)q * N + rank] = X.ex.ext[cnd];
-#endif
         a.out_scores[(size_t)q * N + rank] = bits_score(my.s);
       }
       return min(n, N);
@@ -707,21 +705,6 @@ __device__ __forceinline__ void phase0_next(const IndexView& ix, const PredictAr
     S.d_idx[pos] = my_idx; S.d_pos[pos] = (uint8_t)lane;
   }
   if (lane == 0) { nx.nd = (uint32_t)__popc(known); nx.u = (uint32_t)__popc(uniq); nx.L = L; nx.ok = 1u; }
-#ifndef VMIS_NO_LIST_PREFETCH
-  // pull the heads of the next query's posting lists towards L2 while this query is still inserting: phase 1 then
-  // starts on warm lines instead of two dependent HBM round trips (post_ref, then the list).  Local shards only.
-  if (ix.n_shards == 1) {
-    uint2 ref = make_uint2(0u, 0u);
-    if (my_idx != kEmpty) ref = ix.post_ref[my_idx];
-    for (uint32_t src = known; src != 0u; src &= src - 1u) {
-      const int from = __ffs((int)src) - 1;
-      const uint32_t off4 = __shfl_sync(kFull, ref.x, from), len = __shfl_sync(kFull, ref.y, from);
-      const uint32_t lines = (min(len, a.m) * 4u + 127u) >> 7;                    // 128-byte lines of the list's first m entries
-      const unsigned char* base = reinterpret_cast<const unsigned char*>(ix.post_shard[0] + (size_t)off4 * 4);
-      for (uint32_t l = lane; l < lines; l += 32u) prefetch_l2(base + (size_t)l * 128u);
-    }
-  }
-#endif
 }
 
 __global__ void __launch_bounds__(kThreads, kCtasPerSm)
@@ -829,7 +812,7 @@ vmis_predict_kernel(const IndexView ix, const PredictArgs a, const LaunchPlan pl
       if (nd == 1) {
         // single distinct known item: S = first m postings, all similarities equal → N = first k
         nn = min(n0, K);
-        for (uint32_t i = tid; i < nn; i += kThreads) { const uint32_t sid = P0[i]; nbr_sid[i] = sid; nbr_low[i] = low0; prefetch_l2(ix.sess_ref + sid); }
+        for (uint32_t i = tid; i < nn; i += kThreads) { const uint32_t sid = P0[i]; nbr_sid[i] = sid; nbr_low[i] = low0; PF_SESSREF(ix.sess_ref + sid); }
       } else {
         uint64_t* acc = acc0;
         uint64_t* out = acc1;
@@ -906,7 +889,7 @@ vmis_predict_kernel(const IndexView ix, const PredictArgs a, const LaunchPlan pl
           nn = na;
           for (uint32_t i = tid; i < na; i += kThreads) {
             const uint64_t e = acc[i];
-            nbr_sid[i] = (uint32_t)(e >> 32); nbr_low[i] = (uint32_t)e; prefetch_l2(ix.sess_ref + (uint32_t)(e >> 32));
+            nbr_sid[i] = (uint32_t)(e >> 32); nbr_low[i] = (uint32_t)e; PF_SESSREF(ix.sess_ref + (uint32_t)(e >> 32));
           }
         } else {
           // v* = max v with count(num >= v) >= K  (numerators are >= 1)
@@ -987,9 +970,9 @@ vmis_predict_kernel(const IndexView ix, const PredictArgs a, const LaunchPlan pl
             const uint64_t e = acc[i];
             const uint32_t nm = (uint32_t)e & kNumMask;
             if (nm > vstar) {
-              nbr_sid[gpos] = (uint32_t)(e >> 32); nbr_low[gpos] = (uint32_t)e; ++gpos; prefetch_l2(ix.sess_ref + (uint32_t)(e >> 32));
+              nbr_sid[gpos] = (uint32_t)(e >> 32); nbr_low[gpos] = (uint32_t)e; ++gpos; PF_SESSREF(ix.sess_ref + (uint32_t)(e >> 32));
             } else if (nm == vstar) {
-              if (pre_e < quota) { nbr_sid[tot_g + pre_e] = (uint32_t)(e >> 32); nbr_low[tot_g + pre_e] = (uint32_t)e; prefetch_l2(ix.sess_ref + (uint32_t)(e >> 32)); }
+              if (pre_e < quota) { nbr_sid[tot_g + pre_e] = (uint32_t)(e >> 32); nbr_low[tot_g + pre_e] = (uint32_t)e; PF_SESSREF(ix.sess_ref + (uint32_t)(e >> 32)); }
               ++pre_e;
             }
           }
@@ -1021,8 +1004,13 @@ vmis_predict_kernel(const IndexView ix, const PredictArgs a, const LaunchPlan pl
     VMIS_CLK(S);
     // ------------------------------------------------------------------ phase 2a: neighbour directory
     // the first neighbour's item list ref is requested before the table is cleared: the clear hides its latency
+    // Every thread owns a CONTIGUOUS run of neighbours, so the granules are numbered in neighbour order: the warps of
+    // phase 2b then read the per-neighbour arrays at (nearly) consecutive indices (a strided assignment put
+    // neighbours t and t + 256 next to each other — same bank — and cost 2.7 wavefronts per read).
+    const uint32_t n_own = (nn + kThreads - 1) / kThreads;
+    const uint32_t i0 = min((uint32_t)tid * n_own, nn), i1 = min(i0 + n_own, nn);
     uint2 r_first = make_uint2(0u, 0u);
-    if ((uint32_t)tid < nn) r_first = ix.sess_ref[nbr_sid[tid]];
+    if (i0 < i1) r_first = ix.sess_ref[nbr_sid[i0]];
     {
       // all ones = empty; the capacity is a multiple of 4096: 16-byte stores
       uint4* t4 = reinterpret_cast<uint4*>(stab);
@@ -1030,13 +1018,11 @@ vmis_predict_kernel(const IndexView ix, const PredictArgs a, const LaunchPlan pl
       for (uint32_t i = tid; i < n4; i += kThreads) t4[i] = make_uint4(kEmpty, kEmpty, kEmpty, kEmpty);
     }
     if (tid == 0) { S.n_occ = 0; S.overflow = 0; S.round = 0; }
-    // neighbours tid, tid + 256, ...: item list refs, weights, granule counts (the order of the neighbours is free)
+    // item list refs, weights, granule counts of this thread's neighbours
     uint32_t my_g = 0, my_len = 0;
-    for (uint32_t i = tid; i < nn; i += kThreads) {
-      const uint2 r = i == (uint32_t)tid ? r_first : ix.sess_ref[nbr_sid[i]];
+    for (uint32_t i = i0; i < i1; ++i) {
+      const uint2 r = i == i0 ? r_first : ix.sess_ref[nbr_sid[i]];
       const uint32_t* items = ix.sess_items + (size_t)r.x * 4;
-      prefetch_l2(items);                                           // the inserts read this list next
-      if (r.y > 4u) prefetch_l2(items + (r.y - 1u));
       nbr_goff[i] = r.x; nbr_len[i] = r.y; my_g += (r.y + 3u) >> 2; my_len += r.y;
       uint32_t low = nbr_low[i];
       if (!pos_from_lists) {                                        // reference scan (mod.rs:133-138)
@@ -1063,7 +1049,7 @@ vmis_predict_kernel(const IndexView ix, const PredictArgs a, const LaunchPlan pl
     }
     const bool flat = G <= plan.gran_cap;
     if (flat) {
-      for (uint32_t i = tid; i < nn; i += kThreads) {
+      for (uint32_t i = i0; i < i1; ++i) {
         const uint32_t ng = (nbr_len[i] + 3u) >> 2;
         nbr_goff[i] -= run;
         for (uint32_t g = run; g < run + ng; ++g) gran_nbr[g] = (uint16_t)i;
@@ -1092,7 +1078,8 @@ vmis_predict_kernel(const IndexView ix, const PredictArgs a, const LaunchPlan pl
       __syncthreads();
       VMIS_CLK(S);
       if (!S.overflow && S.n_occ <= plan.occ_cap) {
-        written = select_table(ix, a, S, X, reinterpret_cast<uint32_t*>(gran_nbr), c, stab, plan.tab_cap);
+        written = a.biz ? select_table<true>(ix, a, S, X, reinterpret_cast<uint32_t*>(gran_nbr), c, stab, plan.tab_cap)
+                        : select_table<false>(ix, a, S, X, reinterpret_cast<uint32_t*>(gran_nbr), c, stab, plan.tab_cap);
       } else {
         // redo on a table in HBM sized for THIS query (every item of every neighbour distinct): the CTA's own
         // overflow table, or — a neighbourhood of very long sessions — the one huge table, taken under a lock.
