@@ -1,30 +1,29 @@
 // serenade_b200/csrc/predict_sm100.cu — the VMIS-kNN predict_next kernel for sm_100a.
 //
 // Persistent CTAs (5 per SM, 256 threads, ~44 KB shared memory) pull evolving sessions from a global work
-// counter (the next index is always prefetched) and run one query each, end to end in shared memory:
+// counter (the next two indices are always in flight) and run one query each, end to end in shared memory:
 //
-//   phase 0  de-duplicate the evolving session (vmis_index.rs:335-348), translate external item ids
-//            through the HBM item hash; one packed block scan orders the distinct known items
-//   phase 1  m-sample: the time-descending posting lists of the distinct items (local HBM, or a peer
-//            GPU's HBM over NVLink when the index is item-sharded) are streamed into shared memory by
-//            TMA bulk copies (cp.async.bulk + mbarrier, double buffered) and folded one by one with a
-//            block-wide merge-path merge that de-duplicates, sums the integer similarity numerators,
-//            keeps the first-match position and truncates to the m most recent sessions
-//            (closed form of the heap procedure of vmis_index.rs:344-391)
-//   phase 1b top-k neighbours by (numerator desc, recency desc): packed / ballot histogram or binary
-//            search for the threshold numerator, one ordered scan for the ties (vmis_index.rs:394-412)
-//   phase 2a neighbour directory: item-list refs, integer weight 10·linear_score·numerator
-//            (mod.rs:133-142, :110-116), flat entry → neighbour map (bitmap + word directory)
-//   phase 2b A[item] += weight for every item of every neighbour (mod.rs:144-153): persistent lanes —
-//            a lane whose insert finished takes the next flat entry (dealt by ballot rank, prefetched a
-//            trip ahead), a lane that hit a foreign key steps on; double-hashing inserts into a 4096-slot
-//            shared table; every warp keeps the list of slots it claimed; rare overflow → the CTA's
-//            global table
-//   phase 3  drop the current item (mod.rs:157-160), business rules (:162-182), top-n by (score desc,
-//            item id asc) (mod.rs:185-214): fp32 coarse keys through a u32 warp-bitonic network with a
-//            shared lower bound (tightened per warp by its running n-th best), per-warp lists merged as
-//            a tree, the 32 survivors rescored exactly (f64 g(idf)·A/(10·u)) and sorted once; a margin
-//            test proves the survivors contain the exact top-n, else an exact 96-bit network runs
+//   phase 0  de-duplicate the evolving session (vmis_index.rs:335-348), translate external item ids through the
+//            HBM item hash.  For sessions of <= 32 items the LAST WARP does this for the NEXT query while the other
+//            warps insert (phase 2b hands its rounds out dynamically, so nobody waits for it)
+//   phase 1  m-sample: the time-descending posting lists of the distinct items (local HBM, or a peer GPU's HBM over
+//            NVLink when the index is item-sharded) are streamed into shared memory by TMA bulk copies
+//            (cp.async.bulk + mbarrier, double buffered) and folded one by one with a block-wide merge-path merge
+//            that de-duplicates, sums the integer similarity numerators, keeps the first-match position and
+//            truncates to the m most recent sessions (closed form of the heap procedure of vmis_index.rs:344-391)
+//   phase 1b top-k neighbours by (numerator desc, recency desc): packed / ballot histogram or binary search for the
+//            threshold numerator, one ordered scan for the ties (vmis_index.rs:394-412)
+//   phase 2a neighbour directory: item-list refs, integer weight 10·linear_score·numerator (mod.rs:133-142,
+//            :110-116), granule -> neighbour map (a granule = 16 bytes = up to four items of one item list)
+//   phase 2b A[item] += weight for every item of every neighbour (mod.rs:144-153) into a 4096-slot shared table of
+//            64-bit slots {item | A}: a claim is ONE ATOMS.CAS.64, a hit an add to the low word; rounds of 32
+//            granules per warp from a block-wide counter; the four first probes of a lane are in flight together;
+//            collided items are re-dealt one per lane through a staging row.  Rare overflow -> a table in HBM
+//   phase 3  drop the current item (mod.rs:157-160), business rules (:162-182), top-n by (score desc, item id asc)
+//            (mod.rs:185-214) straight from the table: fp32 coarse keys for all slots, a block-wide lower bound
+//            from the best thread maxima (REDUX), the few survivors rescored exactly (f64 g(idf)·A/(10·u)) by the
+//            threads that found them and ranked by counting across all warps; a margin test / exact 96-bit
+//            network covers heavy score ties
 //
 // All session/item arithmetic is integer and order independent; the only floating point that reaches the
 // output is one f64 multiply + divide per final candidate, so results are bit-exact against the canonical mode
