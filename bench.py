@@ -447,9 +447,34 @@ def b200_arm(args, rank, world, local_rank):
               "e2e": e2e, "roofline": roofline, "step_ms": [round(x, 3) for x in head["step_ms"]], "index": index_info,
               "numa": numa, "sections": {}}
 
+    # The headline is complete.  The extra sections below must never cost it: each runs under try/except, and a
+    # watchdog prints the line as it stands (and ends the process) if a section hangs, e.g. in a collective.
+    emitted = threading.Event()
+
+    def emit():
+        if not emitted.is_set():
+            emitted.set()
+            if rank == 0:
+                print(json.dumps(result), flush=True)
+
+    def watchdog():
+        if not emitted.wait(args.section_timeout):
+            result["sections"]["watchdog"] = f"extra sections did not finish within {args.section_timeout:.0f}s; line printed as is"
+            emit()
+            os._exit(0)
+
+    threading.Thread(target=watchdog, daemon=True).start()
+
+    def guarded(name, fn, *a):
+        try:
+            return fn(*a)
+        except Exception as e:  # noqa: BLE001 — an extra section must not take the headline down
+            log(f"[rank {rank}] section {name} failed: {type(e).__name__}: {e}")
+            return {"error": f"{type(e).__name__}: {e}"}
+
     # ------------------------------------------------------------------ N = 1 extras
     if world == 1 and want("latency"):
-        result["latency"] = latency_section(sb, lib, gix, batches[0])
+        result["latency"] = guarded("latency", latency_section, sb, lib, gix, batches[0])
     if world == 1 and not args.no_cpu_baseline and items is not None:
         from oracle import vmis_oracle as vo
         t2 = time.time()
@@ -464,21 +489,21 @@ def b200_arm(args, rank, world, local_rank):
         result["parity_check"] = parity_vs_oracle(run, gix, oix, batches[W], d_batches[W], B, out, args.parity_queries, threads)
         del oix
     if world == 1 and want("config2"):
-        result["sections"]["config2"] = section_config2(sb, run, args)
+        result["sections"]["config2"] = guarded("config2", section_config2, sb, run, args)
     if world == 1 and want("config4"):
-        result["sections"]["config4"] = section_device_built(sb, run, "synthetic-582M-6.5M", local_rank, rank, world, args)
+        result["sections"]["config4"] = guarded("config4", section_device_built, sb, run, "synthetic-582M-6.5M", local_rank, rank, world, args)
 
     # ------------------------------------------------------------------ N > 1: item-sharded postings
     if world > 1 and want("item_sharded") and items is not None:
-        result["sections"]["item_sharded"] = section_item_sharded(sb, run, gix, items, off, ts, batches, d_batches, B, out,
-                                                                  rank, world, local_rank, args)
+        result["sections"]["item_sharded"] = guarded("item_sharded", section_item_sharded, sb, run, gix, items, off, ts, batches,
+                                                     d_batches, B, out, rank, world, local_rank, args)
     gix.close()
     del d_batches
     torch.cuda.empty_cache()
-    if world == 8 and want("config5"):
-        result["sections"]["config5"] = section_device_built(sb, run, "synthetic-2.3B-6.5M", local_rank, rank, world, args)
-    if rank == 0:
-        print(json.dumps(result))
+    if (world == 8 or args.config5_workload) and world > 1 and want("config5"):
+        result["sections"]["config5"] = guarded("config5", section_device_built, sb, run,
+                                                args.config5_workload or "synthetic-2.3B-6.5M", local_rank, rank, world, args)
+    emit()
     if world > 1:
         dist.destroy_process_group()
     return 0
@@ -702,6 +727,10 @@ def main():
     ap.add_argument("--parity-queries", type=int, default=4096, help="queries of the in-bench oracle check")
     ap.add_argument("--no-cpu-baseline", action="store_true", help="skip everything that runs the CPU oracle")
     ap.add_argument("--device-build", action="store_true", help="generate + index the workload on the device")
+    ap.add_argument("--config5-workload", default=None, choices=sorted(DEVICE_BUILT),
+                    help="run the config5 section (item-sharded, device-built) at any N > 1 on this workload")
+    ap.add_argument("--section-timeout", type=float, default=420.0,
+                    help="seconds the extra sections may take before the headline line is printed without them")
     ap.add_argument("--sections", default="all",
                     help="extra sections: all | none | comma list of latency,config2,config4,item_sharded,config5")
     args = ap.parse_args()
