@@ -182,11 +182,8 @@ __device__ __forceinline__ void bulk_load(void* dst_smem, const void* src_gmem, 
                    smem_u32(dst_smem)), "l"(src_gmem), "r"(bytes), "r"(smem_u32(bar)) : "memory");
 }
 __device__ __forceinline__ void prefetch_l2(const void* p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
-#ifdef VMIS_NO_PF_SESSREF
-#define PF_SESSREF(p) do {} while (0)
-#else
+// L2 prefetch of a neighbour's session ref as soon as the neighbour is known (A/B: +1.2 %)
 #define PF_SESSREF(p) prefetch_l2(p)
-#endif
 __device__ __forceinline__ void fence_async_proxy() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 
 #ifdef VMIS_PHASE_CLOCKS
@@ -373,7 +370,9 @@ __device__ __forceinline__ void accumulate(const IndexView& ix, SmemLayout& S, c
     // whatever their luck with the probe sequences
     auto grab = [&]() -> uint32_t {
       uint32_t r = 0;
-      if (lane == 0) r = atomicAdd(&S.round, 1u);
+      // one lane, one atomic: written in PTX so that the compiler does not wrap it in its warp-aggregation sequence
+      // (vote, find-leader, popc, shuffle — 19 instructions for a single active lane)
+      if (lane == 0) asm volatile("atom.shared.add.u32 %0, [%1], 1;" : "=r"(r) : "r"(smem_u32(&S.round)) : "memory");
       return __shfl_sync(kFull, r, 0) * 32u;
     };
     uint4 it; int32_t w;
@@ -577,22 +576,8 @@ __device__ __forceinline__ uint32_t select_table(const IndexView& ix, const Pred
         VMIS_CLK(S);
         __syncthreads();
         VMIS_CLK(S);
-#ifdef VMIS_BOUND_BY_RANK
-        // the N-th largest of the (up to 32) published keys by counting: every lane owns one key and counts the keys
-        // above it (broadcast reads, no shuffle chain); keys are unique, so exactly one lane has N - 1 above it
-        const uint32_t mine32 = (lane >> 2) < kWarps ? S.top4[lane >> 2][lane & 3] : 0u;
-        uint32_t above = 0;
-#pragma unroll
-        for (int w = 0; w < kWarps; ++w) {
-          const uint4 t = *reinterpret_cast<const uint4*>(S.top4[w]);
-          above += (t.x > mine32) + (t.y > mine32) + (t.z > mine32) + (t.w > mine32);
-        }
-        const uint32_t hit = __ballot_sync(kFull, mine32 != 0u && above == N - 1u);
-        const uint32_t bound = hit ? __shfl_sync(kFull, mine32, __ffs((int)hit) - 1) >> kIdxBits : 0u;   // 0: fewer than N candidates
-#else
         const uint32_t s32 = u32_sort_desc((lane >> 2) < kWarps ? S.top4[lane >> 2][lane & 3] : 0u, lane);
         const uint32_t bound = __shfl_sync(kFull, s32, (int)N - 1) >> kIdxBits;   // 0: fewer than N candidates so far
-#endif
         thr = bound > 1u ? (bound - 1u) << kIdxBits : 1u;
       }
       uint32_t keep = 0;
@@ -892,13 +877,9 @@ vmis_predict_kernel(const IndexView ix, const PredictArgs a, const LaunchPlan pl
           }
         } else {
           // v* = max v with count(num >= v) >= K  (numerators are >= 1)
-#ifdef VMIS_TOPK_EVEN
-          const uint32_t E = (na + kThreads - 1) / kThreads;     // contiguous chunk per thread keeps recency order
-#else
           // contiguous chunk per thread keeps recency order; an ODD chunk length makes the 64-bit reads of a warp
           // (stride 2 E words) conflict free
           const uint32_t E = ((na + kThreads - 1) / kThreads) | 1u;
-#endif
           const uint32_t e0 = min((uint32_t)tid * E, na), e1 = min(e0 + E, na);
           const uint32_t vmax = L * (L + 1) / 2;
           uint32_t vstar, tot_g;
