@@ -312,7 +312,8 @@ int host_batch(const vmis_index* cix, const uint64_t* q_items, const uint32_t* q
     const int l = e ? std::atoi(e) : 15;
     return 1u << (l < 10 ? 10 : l > 20 ? 20 : l);
   }();
-  constexpr size_t kPipe = 3;
+  // streams in the ring (tuning knob VMIS_PIPE, default 3)
+  static const size_t kPipe = [] { const char* e = std::getenv("VMIS_PIPE"); const int p = e ? std::atoi(e) : 3; return (size_t)(p < 1 ? 1 : p > 8 ? 8 : p); }();
   const uint32_t n_chunks = (n_q + kChunk - 1) / kChunk;
   const size_t n_ctx = stream_ ? 1 : std::min<size_t>(kPipe, n_chunks);
   const size_t width = nb_mode ? k : how_many;

@@ -852,7 +852,9 @@ vmis_predict_kernel(const IndexView ix, const PredictArgs a, const LaunchPlan pl
               rh[s] = takeA ? ak : bk;
               rl[s] = takeA ? (uint32_t)av + (ak == bk ? cj : 0u) : lowj;
               vmask |= (emit ? 1u : 0u) << s;
-              if (takeA) { pak = ak; ++ai; av = acc[ai]; } else { ++bi; bk = lst[bi]; }
+              // no step past the thread's share: the heads would run beyond the sentinels, into the staging buffer a
+              // TMA copy may be filling (harmless values, but a read under an in-flight asynchronous write)
+              if ((uint32_t)s < steps) { if (takeA) { pak = ak; ++ai; av = acc[ai]; } else { ++bi; bk = lst[bi]; } }
             }
             int total;
             uint32_t p = out_count + (uint32_t)block_excl_scan(__popc(vmask), S.scan, par, total);
