@@ -195,11 +195,13 @@ __device__ __forceinline__ void fence_async_proxy() { asm volatile("fence.proxy.
 #define VMIS_CLK_RESET(S) do {} while (0)
 #define VMIS_CLK(S) do {} while (0)
 #endif
+constexpr uint32_t kRefCache = 8;     // items whose post_ref is fetched ahead of phase 1 (sessions of up to 8 distinct items)
 struct SmemLayout {
   VMIS_CLK_FIELDS
   // fixed part
   uint32_t d_idx[kMaxSessionLen];    // distinct known items, most recent first
   uint8_t d_pos[kMaxSessionLen];
+  uint2 d_ref[kRefCache];            // posting-list refs of the first distinct items, loaded while the previous query inserts
   ScanScratch scan;
   uint32_t nd;
   // the query this CTA runs next (double buffered): thread 0 publishes `q` while the current query is in phase 1;
@@ -688,6 +690,14 @@ __device__ __forceinline__ void phase0_next(const IndexView& ix, const PredictAr
     const uint32_t pos = (uint32_t)__popc(known & ((1u << lane) - 1u));
     S.d_idx[pos] = my_idx; S.d_pos[pos] = (uint8_t)lane;
   }
+  if (my_idx != kEmpty) {
+    // the posting-list ref of the item: one dependent global load less at the head of phase 1 and of every fold
+    const uint32_t pos = (uint32_t)__popc(known & ((1u << lane) - 1u));
+    if (pos < kRefCache) {
+      const uint2 ref = ix.post_ref[my_idx];
+      S.d_ref[pos] = ref;
+    }
+  }
   if (lane == 0) { nx.nd = (uint32_t)__popc(known); nx.u = (uint32_t)__popc(uniq); nx.L = L; nx.ok = 1u; }
 }
 
@@ -771,7 +781,10 @@ vmis_predict_kernel(const IndexView ix, const PredictArgs a, const LaunchPlan pl
         const int flag = (my_idx != kEmpty) ? 1 : 0;
         int total;
         const int pos = block_excl_scan(flag | ((distinct ? 1 : 0) << 16), S.scan, par, total) & 0xFFFF;
-        if (flag) { S.d_idx[pos] = my_idx; S.d_pos[pos] = (uint8_t)tid; }
+        if (flag) {
+          S.d_idx[pos] = my_idx; S.d_pos[pos] = (uint8_t)tid;
+          if ((uint32_t)pos < kRefCache) S.d_ref[pos] = ix.post_ref[my_idx];
+        }
         if (tid == 0) S.nd = (uint32_t)total & 0xFFFFu;
         u = (uint32_t)total >> 16;
       }
@@ -788,7 +801,7 @@ vmis_predict_kernel(const IndexView ix, const PredictArgs a, const LaunchPlan pl
     VMIS_CLK(S);
     if (nd > 0 && K > 0 && M > 0 && (N > 0 || neighbors_mode)) {
       // ---------------------------------------------------------------- phase 1
-      const uint2 ref0 = ix.post_ref[S.d_idx[0]];
+      const uint2 ref0 = S.d_ref[0];
       const uint32_t n0 = min(ref0.y, M);
       const uint32_t* P0 = posting_list(ix, S.d_idx[0], ref0.x);
       const uint32_t low0 = (S.d_pos[0] << 24) | (L - S.d_pos[0]);
@@ -802,7 +815,7 @@ vmis_predict_kernel(const IndexView ix, const PredictArgs a, const LaunchPlan pl
         uint64_t* out = acc1;
         // TMA: lists 1 and 2 start streaming into the two staging buffers while list 0 is converted
         auto issue = [&](uint32_t j, uint32_t b) {
-          const uint2 ref = ix.post_ref[S.d_idx[j]];
+          const uint2 ref = j < kRefCache ? S.d_ref[j] : ix.post_ref[S.d_idx[j]];
           const uint32_t bytes = ((min(min(ref.y, M), plan.list_cap) + 3u) & ~3u) * 4u;
           mbar_expect_tx(&S.bar[b], bytes);
           bulk_load(listbuf + (size_t)b * plan.list_cap, posting_list(ix, S.d_idx[j], ref.x), bytes, &S.bar[b]);
@@ -814,7 +827,7 @@ vmis_predict_kernel(const IndexView ix, const PredictArgs a, const LaunchPlan pl
         for (uint32_t j = 1; j < nd; ++j) {
           const uint32_t bsel = (j - 1) & 1u;
           const uint32_t* lst = listbuf + (size_t)bsel * plan.list_cap;
-          const uint2 ref = ix.post_ref[S.d_idx[j]];
+          const uint2 ref = j < kRefCache ? S.d_ref[j] : ix.post_ref[S.d_idx[j]];
           const uint32_t nb = min(min(ref.y, M), plan.list_cap);
           const uint32_t cj = L - S.d_pos[j];
           const uint32_t lowj = (S.d_pos[j] << 24) | cj;
