@@ -3,9 +3,9 @@
 //
 // The build produces exactly the arrays of IndexView (vmis_device.h) from training sessions that already live
 // in HBM: time-rank the kept sessions (radix sort of (timestamp, session idx)), build the item dictionary
-// (radix sort + unique of the external ids, device hash table), emit the session→items lists (dense, ascending,
-// 16-byte aligned) and the item→sessions posting lists (radix sort of (item, ~rank), truncate to m, shard by
-// item).  idf needs `ln`: the document frequencies go to the host and idf is computed there with the same libm
+// (hash set of the external ids, radix sort of the distinct ones, device hash table), emit the session→items lists (dense, ascending,
+// 16-byte aligned) and the item→sessions posting lists (stable radix sort of the rank-ordered (item, rank) pairs on
+// the item bits, truncate to m, shard by item).  idf needs `ln`: the document frequencies go to the host and idf is computed there with the same libm
 // as the CPU oracle, so scores stay bit-identical to the host-built index.  Sorting uses CUB's device radix sort
 // (a plain library sort, not a hot-path kernel); every other step is a kernel in this file.
 #include <cub/cub.cuh>
@@ -13,6 +13,7 @@
 #include <algorithm>
 #include <cmath>
 #include <string>
+#include <thread>
 #include <vector>
 
 #include "build_device.h"
@@ -68,23 +69,45 @@ __global__ void k_rank_lengths(const uint64_t* sorted_keys, const uint64_t* off,
   elen[r] = len; plen[r] = (len + 3) & ~3ull;
 }
 
-// external ids of all kept entries, in rank order (input of the dictionary sort)
-__global__ void k_gather_ext(const uint64_t* items, const uint64_t* off, const uint32_t* rank_to_orig, const uint64_t* estart,
-                             uint64_t Sk, uint64_t* ext_flat) {
+// ---- item dictionary by hashing: every external id of the kept sessions goes into an open-addressing SET (8-byte
+// slots, all ones = empty); most probes end on a plain load because the id is already there (60 M interactions hold
+// 1.7 M distinct items), so there are few atomics and no 64-bit sort of all interactions (that sort was 4.4 of the
+// build's 13.6 ms in round 1).  The distinct ids are then collected and only THEY are sorted.
+constexpr unsigned long long kNoKey = ~0ull;
+__global__ void k_dedup_insert(const uint64_t* items, const uint64_t* off, const uint32_t* rank_to_orig, uint64_t Sk,
+                               unsigned long long* set, uint64_t mask, unsigned long long* n_distinct, unsigned int* flags) {
   const uint64_t r = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (r >= Sk) return;
   const uint32_t o = rank_to_orig[r];
-  const uint64_t b = off[o], n = off[o + 1] - b, e = estart[r];
-  for (uint64_t t = 0; t < n; ++t) ext_flat[e + t] = items[b + t];
+  const uint64_t b = off[o], n = off[o + 1] - b;
+  for (uint64_t t = 0; t < n; ++t) {
+    const unsigned long long k = items[b + t];
+    if (k == kNoKey) { flags[0] = 1u; continue; }                      // the one id that collides with "empty"
+    uint64_t h = hash_u64_dev(k) & mask;
+    for (;;) {
+      unsigned long long cur = set[h];
+      if (cur == k) break;
+      if (cur == kNoKey) {
+        cur = atomicCAS(&set[h], kNoKey, k);
+        if (cur == kNoKey) { if (atomicAdd(n_distinct, 1ull) + 1 > (mask + 1) / 2) flags[1] = 1u; break; }   // over half full: retry bigger
+        if (cur == k) break;
+      }
+      h = (h + 1) & mask;
+    }
+    if (flags[1]) return;
+  }
 }
-
-__global__ void k_flag_heads(const uint64_t* sorted, uint64_t n, uint64_t* flags) {
+__global__ void k_dedup_collect(const unsigned long long* set, uint64_t cap, uint64_t* uniq, unsigned long long* cursor) {
   const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (i < n) flags[i] = (i == 0 || sorted[i] != sorted[i - 1]) ? 1ull : 0ull;
-}
-__global__ void k_scatter_unique(const uint64_t* sorted, const uint64_t* flags, const uint64_t* pos, uint64_t n, uint64_t* uniq) {
-  const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (i < n && flags[i]) uniq[pos[i]] = sorted[i];
+  const unsigned long long k = i < cap ? set[i] : kNoKey;
+  const bool have = k != kNoKey;
+  const unsigned m = __ballot_sync(0xFFFFFFFFu, have);
+  if (!m) return;
+  unsigned long long base = 0;
+  const int lane = threadIdx.x & 31, leader = __ffs((int)m) - 1;
+  if (lane == leader) base = atomicAdd(cursor, (unsigned long long)__popc(m));
+  base = __shfl_sync(0xFFFFFFFFu, base, leader);
+  if (have) uniq[base + __popc(m & ((1u << lane) - 1u))] = k;
 }
 
 __global__ void k_hash_clear(ItemHashEntry* tab, uint64_t cap) {
@@ -115,7 +138,7 @@ __device__ __forceinline__ uint32_t hash_lookup(const ItemHashEntry* tab, uint32
 // (item, ~rank) keys whose sort yields the posting lists
 __global__ void k_emit_sessions(const uint64_t* items, const uint64_t* off, const uint32_t* rank_to_orig, const uint64_t* estart,
                                 const uint64_t* pstart, uint64_t Sk, const ItemHashEntry* tab, uint32_t mask, uint2* sess_ref,
-                                uint32_t* sess_items, uint64_t* post_keys, unsigned int* error_flag) {
+                                uint32_t* sess_items, uint32_t* post_item, uint32_t* post_rank, unsigned int* error_flag) {
   const uint64_t r = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (r >= Sk) return;
   const uint32_t o = rank_to_orig[r];
@@ -134,15 +157,15 @@ __global__ void k_emit_sessions(const uint64_t* items, const uint64_t* off, cons
   for (uint32_t t = 0; t < np; ++t) sess_items[ps + t] = t < n ? idx[t] : kEmpty;
   for (uint32_t t = 0; t < n; ++t) {
     if (t > 0 && idx[t] == idx[t - 1]) atomicExch(error_flag, 1u);       // duplicate item inside a session
-    post_keys[es + t] = ((uint64_t)idx[t] << 32) | (uint64_t)(0xFFFFFFFFu - (uint32_t)r);
+    post_item[es + t] = idx[t]; post_rank[es + t] = (uint32_t)r;          // emitted in rank order: a STABLE sort by item keeps it
   }
 }
 
-__global__ void k_seg_starts(const uint64_t* sorted_keys, uint64_t P, uint32_t I, uint64_t* seg_start) {
+__global__ void k_seg_starts(const uint32_t* sorted_item, uint64_t P, uint32_t I, uint64_t* seg_start) {
   const uint64_t p = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (p >= P) { if (p == P) seg_start[I] = P; return; }
-  const uint32_t d = (uint32_t)(sorted_keys[p] >> 32);
-  if (p == 0 || d != (uint32_t)(sorted_keys[p - 1] >> 32)) seg_start[d] = p;
+  const uint32_t d = sorted_item[p];
+  if (p == 0 || d != sorted_item[p - 1]) seg_start[d] = p;
 }
 
 // per item: df, truncated length, padded length written at its shard-major position
@@ -163,16 +186,17 @@ __global__ void k_post_ref(const uint64_t* scan_t, const uint32_t* df, uint32_t 
   const uint64_t rel = scan_t[(uint64_t)sh * per_shard + d / n_shards] - scan_t[(uint64_t)sh * per_shard];
   post_ref[d] = make_uint2((uint32_t)(rel >> 2), (uint32_t)((uint64_t)df[d] < m ? df[d] : m));
 }
-__global__ void k_fill_postings(const uint64_t* sorted_keys, uint64_t P, const uint64_t* seg_start, const uint2* post_ref,
-                                uint32_t shard, uint32_t n_shards, uint32_t* postings) {
+// an item's segment holds its sessions in rank-ASCENDING order (stable sort of rank-ordered input): the posting list
+// is its last min(df, m) entries, most recent first
+__global__ void k_fill_postings(const uint32_t* sorted_item, const uint32_t* sorted_rank, uint64_t P, const uint64_t* seg_start,
+                                const uint2* post_ref, uint32_t shard, uint32_t n_shards, uint32_t* postings) {
   const uint64_t p = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (p >= P) return;
-  const uint64_t key = sorted_keys[p];
-  const uint32_t d = (uint32_t)(key >> 32);
+  const uint32_t d = sorted_item[p];
   if (d % n_shards != shard) return;
-  const uint64_t j = p - seg_start[d];
+  const uint64_t j = seg_start[d + 1] - 1 - p;                   // 0 = the most recent session of the item
   const uint2 ref = post_ref[d];
-  if (j < ref.y) postings[(uint64_t)ref.x * 4 + j] = 0xFFFFFFFFu - (uint32_t)key;
+  if (j < ref.y) postings[(uint64_t)ref.x * 4 + j] = sorted_rank[p];
 }
 __global__ void k_fill_u8(uint8_t* p, uint64_t n, uint8_t v) {
   const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -208,6 +232,16 @@ bool radix_sort_keys(KeyT* in, KeyT* out, uint64_t n, int end_bit, cudaStream_t 
   DevBuf tmp;
   CU_OK(tmp.alloc(tb));
   CU_OK(cub::DeviceRadixSort::SortKeys(tmp.p, tb, in, out, (long long)n, 0, end_bit, st));
+  CU_OK(cudaStreamSynchronize(st));
+  return true;
+}
+bool radix_sort_pairs_u32(uint32_t* k_in, uint32_t* k_out, uint32_t* v_in, uint32_t* v_out, uint64_t n, int end_bit,
+                          cudaStream_t st, std::string* err) {
+  size_t tb = 0;
+  CU_OK(cub::DeviceRadixSort::SortPairs(nullptr, tb, k_in, k_out, v_in, v_out, (long long)n, 0, end_bit, st));
+  DevBuf tmp;
+  CU_OK(tmp.alloc(tb));
+  CU_OK(cub::DeviceRadixSort::SortPairs(tmp.p, tb, k_in, k_out, v_in, v_out, (long long)n, 0, end_bit, st));
   CU_OK(cudaStreamSynchronize(st));
   return true;
 }
@@ -284,29 +318,39 @@ bool build_index_device(const DeviceSessions& s, uint64_t m, uint64_t max_len, d
   keys2.free_now(); elen.free_now(); plen.free_now();
   if ((Ppad >> 2) > 0xFFFFFFFFull) { *err = "session item array too large"; return false; }
 
-  // 2. item dictionary: sorted unique external ids
-  DevBuf ext, ext_sorted, flags, pos, item_key;
-  CU_OK(ext.alloc(P * 8)); CU_OK(ext_sorted.alloc(P * 8));
-  k_gather_ext<<<blocks_for(Sk), kB, 0, st>>>(s.items, s.off, rank_to_orig.as<uint32_t>(), estart.as<uint64_t>(), Sk,
-                                              ext.as<uint64_t>());
-  CU_OK(cudaGetLastError());
-  if (!radix_sort_keys(ext.as<uint64_t>(), ext_sorted.as<uint64_t>(), P, 64, st, err)) return false;
-  ext.free_now();
-  CU_OK(flags.alloc((P + 1) * 8)); CU_OK(pos.alloc((P + 1) * 8));
-  CU_OK(cudaMemsetAsync(flags.p, 0, (P + 1) * 8, st));
-  k_flag_heads<<<blocks_for(P), kB, 0, st>>>(ext_sorted.as<uint64_t>(), P, flags.as<uint64_t>());
-  CU_OK(cudaGetLastError());
-  if (!exclusive_scan_u64(flags.as<uint64_t>(), pos.as<uint64_t>(), P + 1, st, err)) return false;
-  uint64_t I64 = 0;
-  CU_OK(cudaMemcpy(&I64, pos.as<uint64_t>() + P, 8, cudaMemcpyDeviceToHost));
-  if (I64 >= 0x7FFFFFFFull) { *err = "too many items"; return false; }
-  const uint32_t I = (uint32_t)I64;
-  CU_OK(item_key.alloc((uint64_t)I * 8));
-  k_scatter_unique<<<blocks_for(P), kB, 0, st>>>(ext_sorted.as<uint64_t>(), flags.as<uint64_t>(), pos.as<uint64_t>(), P,
-                                                 item_key.as<uint64_t>());
-  CU_OK(cudaGetLastError());
-  CU_OK(cudaStreamSynchronize(st));
-  ext_sorted.free_now(); flags.free_now(); pos.free_now();
+  // 2. item dictionary: distinct external ids through a hash set, then a sort of the distinct ids only
+  DevBuf item_key;
+  uint32_t I = 0;
+  {
+    DevBuf set, uniq, uniq_sorted, cnt2;
+    CU_OK(cnt2.alloc(32));
+    uint64_t cap = 1ull << 22;
+    while (cap < P / 8) cap <<= 1;
+    for (;;) {
+      CU_OK(set.alloc(cap * 8));
+      CU_OK(cudaMemsetAsync(set.p, 0xFF, cap * 8, st));
+      CU_OK(cudaMemsetAsync(cnt2.p, 0, 32, st));
+      k_dedup_insert<<<blocks_for(Sk), kB, 0, st>>>(s.items, s.off, rank_to_orig.as<uint32_t>(), Sk, set.as<unsigned long long>(),
+                                                     cap - 1, cnt2.as<unsigned long long>(), cnt2.as<unsigned int>() + 4);
+      CU_OK(cudaGetLastError());
+      unsigned long long hdr[3];                                     // [0] distinct, [1] collect cursor, [2] flags (2 x u32)
+      CU_OK(cudaMemcpy(hdr, cnt2.p, 24, cudaMemcpyDeviceToHost));
+      const unsigned int has_max = (unsigned int)(hdr[2] & 0xFFFFFFFFu), overfull = (unsigned int)(hdr[2] >> 32);
+      if (overfull) { if (cap >= 4 * P + 1024) { *err = "item dictionary: hash set overflow"; return false; } cap <<= 2; continue; }
+      const uint64_t I64 = hdr[0] + (has_max ? 1 : 0);
+      if (I64 == 0 || I64 >= 0x7FFFFFFFull) { *err = I64 ? "too many items" : "no items"; return false; }
+      I = (uint32_t)I64;
+      CU_OK(uniq.alloc((uint64_t)I * 8)); CU_OK(uniq_sorted.alloc((uint64_t)I * 8));
+      k_dedup_collect<<<blocks_for(cap), kB, 0, st>>>(set.as<unsigned long long>(), cap, uniq.as<uint64_t>(),
+                                                      cnt2.as<unsigned long long>() + 1);
+      CU_OK(cudaGetLastError());
+      if (has_max) { const unsigned long long mx = kNoKey; CU_OK(cudaMemcpyAsync(uniq.as<uint64_t>() + hdr[0], &mx, 8, cudaMemcpyHostToDevice, st)); }
+      set.free_now();
+      if (!radix_sort_keys(uniq.as<uint64_t>(), uniq_sorted.as<uint64_t>(), I, 64, st, err)) return false;
+      uniq_sorted.release_to(&item_key.p);
+      break;
+    }
+  }
 
   // 3. device item hash
   uint64_t cap = 16; while (cap < (uint64_t)I * 2) cap <<= 1;
@@ -317,31 +361,34 @@ bool build_index_device(const DeviceSessions& s, uint64_t m, uint64_t max_len, d
   CU_OK(cudaGetLastError());
 
   // 4. session → items, and the posting sort keys
-  DevBuf sess_ref, sess_items, pkeys, pkeys_sorted, eflag;
+  DevBuf sess_ref, sess_items, p_item, p_rank, p_item_sorted, p_rank_sorted, eflag;
   CU_OK(sess_ref.alloc(Sk * sizeof(uint2))); CU_OK(sess_items.alloc(Ppad * 4));
-  CU_OK(pkeys.alloc(P * 8)); CU_OK(eflag.alloc(4));
+  CU_OK(p_item.alloc(P * 4)); CU_OK(p_rank.alloc(P * 4)); CU_OK(eflag.alloc(4));
   CU_OK(cudaMemsetAsync(eflag.p, 0, 4, st));
   k_emit_sessions<<<blocks_for(Sk), kB, 0, st>>>(s.items, s.off, rank_to_orig.as<uint32_t>(), estart.as<uint64_t>(),
                                                  pstart.as<uint64_t>(), Sk, item_hash.as<ItemHashEntry>(), (uint32_t)(cap - 1),
-                                                 sess_ref.as<uint2>(), sess_items.as<uint32_t>(), pkeys.as<uint64_t>(),
-                                                 eflag.as<unsigned int>());
+                                                 sess_ref.as<uint2>(), sess_items.as<uint32_t>(), p_item.as<uint32_t>(),
+                                                 p_rank.as<uint32_t>(), eflag.as<unsigned int>());
   CU_OK(cudaGetLastError());
   unsigned int ef = 0;
   CU_OK(cudaMemcpy(&ef, eflag.p, 4, cudaMemcpyDeviceToHost));
   if (ef) { *err = "duplicate item inside a training session"; return false; }
   estart.free_now(); pstart.free_now();
 
-  // 5. item → sessions: sort (item, ~rank), truncate to m, shard by item
-  CU_OK(pkeys_sorted.alloc(P * 8));
-  if (!radix_sort_keys(pkeys.as<uint64_t>(), pkeys_sorted.as<uint64_t>(), P, 32 + bits_for(I), st, err)) return false;
-  pkeys.free_now();
+  // 5. item → sessions: the (item, rank) pairs were emitted in rank order, so a STABLE radix sort on the item bits
+  //    alone (3 digit passes for 21-bit dense ids instead of 7 over 53-bit composite keys) leaves every item's
+  //    sessions in rank order; truncate to m, shard by item
+  CU_OK(p_item_sorted.alloc(P * 4)); CU_OK(p_rank_sorted.alloc(P * 4));
+  if (!radix_sort_pairs_u32(p_item.as<uint32_t>(), p_item_sorted.as<uint32_t>(), p_rank.as<uint32_t>(), p_rank_sorted.as<uint32_t>(),
+                            P, bits_for(I), st, err)) return false;
+  p_item.free_now(); p_rank.free_now();
   DevBuf seg_start, df, padded_t, scan_t, post_ref, postings;
   const uint32_t per_shard = (I + n_shards - 1) / n_shards;
   const uint64_t nt = (uint64_t)per_shard * n_shards + 1;
   CU_OK(seg_start.alloc(((uint64_t)I + 1) * 8)); CU_OK(df.alloc((uint64_t)I * 4));
   CU_OK(padded_t.alloc(nt * 8)); CU_OK(scan_t.alloc(nt * 8)); CU_OK(post_ref.alloc((uint64_t)I * sizeof(uint2)));
   CU_OK(cudaMemsetAsync(padded_t.p, 0, nt * 8, st));
-  k_seg_starts<<<blocks_for(P + 1), kB, 0, st>>>(pkeys_sorted.as<uint64_t>(), P, I, seg_start.as<uint64_t>());
+  k_seg_starts<<<blocks_for(P + 1), kB, 0, st>>>(p_item_sorted.as<uint32_t>(), P, I, seg_start.as<uint64_t>());
   k_post_len<<<blocks_for(I), kB, 0, st>>>(seg_start.as<uint64_t>(), I, m, n_shards, per_shard, df.as<uint32_t>(),
                                            padded_t.as<uint64_t>());
   CU_OK(cudaGetLastError());
@@ -356,11 +403,11 @@ bool build_index_device(const DeviceSessions& s, uint64_t m, uint64_t max_len, d
   if ((shard_entries >> 2) > 0xFFFFFFFFull) { *err = "posting array too large"; return false; }
   CU_OK(postings.alloc(shard_entries * 4));
   CU_OK(cudaMemsetAsync(postings.p, 0xFF, std::max<uint64_t>(shard_entries * 4, 16), st));
-  k_fill_postings<<<blocks_for(P), kB, 0, st>>>(pkeys_sorted.as<uint64_t>(), P, seg_start.as<uint64_t>(), post_ref.as<uint2>(),
-                                                shard, n_shards, postings.as<uint32_t>());
+  k_fill_postings<<<blocks_for(P), kB, 0, st>>>(p_item_sorted.as<uint32_t>(), p_rank_sorted.as<uint32_t>(), P, seg_start.as<uint64_t>(),
+                                                post_ref.as<uint2>(), shard, n_shards, postings.as<uint32_t>());
   CU_OK(cudaGetLastError());
   CU_OK(cudaStreamSynchronize(st));
-  pkeys_sorted.free_now(); seg_start.free_now(); padded_t.free_now(); scan_t.free_now();
+  p_item_sorted.free_now(); p_rank_sorted.free_now(); seg_start.free_now(); padded_t.free_now(); scan_t.free_now();
 
   // 6. idf on the host (same libm as the oracle), attributes, host copies for the accessors
   std::vector<uint32_t> h_df(I);
@@ -368,18 +415,29 @@ bool build_index_device(const DeviceSessions& s, uint64_t m, uint64_t max_len, d
   df.free_now();
   out->host_idf.resize(I);
   uint64_t n_post = 0;
-  for (uint32_t d = 0; d < I; ++d) {
-    out->host_idf[d] = std::log((double)P / (double)h_df[d]) * idf_weighting;      // vmis_index.rs:509-513
-    n_post += std::min<uint64_t>(h_df[d], m);
+  {
+    // ln on the host (the oracle's libm), spread over the cores: 1.7 M logarithms are 15 ms on one thread
+    const unsigned nt = std::max(1u, std::min(16u, std::thread::hardware_concurrency()));
+    std::vector<uint64_t> part(nt, 0);
+    std::vector<std::thread> th;
+    for (unsigned t = 0; t < nt; ++t) th.emplace_back([&, t]() {
+      const uint32_t lo = (uint32_t)((uint64_t)I * t / nt), hi = (uint32_t)((uint64_t)I * (t + 1) / nt);
+      uint64_t np = 0;
+      for (uint32_t d = lo; d < hi; ++d) {
+        out->host_idf[d] = std::log((double)P / (double)h_df[d]) * idf_weighting;      // vmis_index.rs:509-513
+        np += std::min<uint64_t>(h_df[d], m);
+      }
+      part[t] = np; });
+    for (auto& x : th) x.join();
+    for (uint64_t v : part) n_post += v;
   }
   DevBuf idf, attr;
   CU_OK(idf.alloc((uint64_t)I * 8)); CU_OK(attr.alloc(I));
   CU_OK(cudaMemcpy(idf.p, out->host_idf.data(), (uint64_t)I * 8, cudaMemcpyHostToDevice));
   k_fill_u8<<<blocks_for(I), kB, 0, st>>>(attr.as<uint8_t>(), I, (uint8_t)(VMIS_ATTR_EXISTS | VMIS_ATTR_FOR_SALE));
   CU_OK(cudaGetLastError());
-  out->host_item_key.resize(I); out->host_item_hash.resize(cap);
+  out->host_item_key.resize(I);                 // the sorted dictionary doubles as the host-side lookup structure
   CU_OK(cudaMemcpy(out->host_item_key.data(), item_key.p, (uint64_t)I * 8, cudaMemcpyDeviceToHost));
-  CU_OK(cudaMemcpy(out->host_item_hash.data(), item_hash.p, cap * sizeof(ItemHashEntry), cudaMemcpyDeviceToHost));
   CU_OK(cudaStreamSynchronize(st));
 
   out->n_items = I; out->n_kept = Sk; out->n_pairs_kept = P; out->n_postings = n_post;

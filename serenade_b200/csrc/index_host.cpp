@@ -245,7 +245,12 @@ bool read_sessions_from_csv(const std::string& path, Sessions* out, std::string*
 }
 
 uint32_t host_lookup_item(const FlatIndex& f, uint64_t item) {
-  if (f.item_hash.empty()) return kEmpty;
+  if (f.item_hash.empty()) {
+    // device-built handle: the hash table lives in HBM only; the dictionary is sorted, and the accessors that come
+    // here (idf, find_attributes, postings) are not on any hot path
+    const auto it = std::lower_bound(f.item_key.begin(), f.item_key.end(), item);
+    return it != f.item_key.end() && *it == item ? (uint32_t)(it - f.item_key.begin()) : kEmpty;
+  }
   const uint32_t mask = (uint32_t)f.item_hash.size() - 1;
   uint32_t h = (uint32_t)mix64(item) & mask;
   for (;;) {
