@@ -542,8 +542,18 @@ def latency_section(sb, lib, gix, batch):
                          sc1.ctypes.data_as(f64p))
         lat.append((time.perf_counter() - t_a) * 1e6)
     lat = np.sort(np.array(lat[100:]))
-    out = {"single_call_us": {p: round(float(np.percentile(lat, float(p[1:]))), 1) for p in ("p50", "p90", "p99")},
-           "note": "vmis_predict, one evolving session per call, host buffers",
+    pct = lambda v: {p: round(float(np.percentile(v, float(p[1:]))), 1) for p in ("p50", "p90", "p99")}
+    # the same calls from a native loop (what a Rust / C++ host sees: no interpreter between the calls)
+    n_nat = 2000
+    nat = np.zeros(n_nat, dtype=np.float32)
+    n_lat_q = min(len(qo0) - 1, 4096)
+    rc = lib.vmis_predict_latency_test(gix.handle, qi0.ctypes.data_as(u64p), qo0.ctypes.data_as(C.POINTER(C.c_uint32)), n_lat_q,
+                                       K, M, HOW_MANY, 0, n_nat, nat.ctypes.data_as(C.POINTER(C.c_float)))
+    if rc != n_nat:
+        raise RuntimeError(f"vmis_predict_latency_test: {rc}")
+    out = {"single_call_us": pct(nat[200:]), "single_call_via_python_us": pct(lat),
+           "note": "vmis_predict, one evolving session per call, host buffers; native loop (vmis_predict_latency_test) and "
+                   "the same call through ctypes",
            "reference_readme": "p90 < 1.7 ms per prediction; 1000 predictions/s on 2 vCPU (README.md:16-17)"}
     n_q = min(len(qo0) - 1, 1 << 16)
     sub = (qi0[:qo0[n_q]], qo0[:n_q + 1])

@@ -284,6 +284,12 @@ void vmis_batcher_destroy(vmis_batcher_t* batcher);
 long long vmis_batcher_load_test(vmis_batcher_t* batcher, const uint64_t* q_items, const uint32_t* q_off, uint32_t n_q,
                                  uint32_t n_threads, double target_rps, uint32_t duration_ms, float* lat_us, size_t cap,
                                  double* achieved_rps);
+/* Closed-loop lone caller (measurement aid for the reference's own call shape, mod.rs:118-125): n_calls vmis_predict()
+ * calls from the calling thread, one evolving session of the CSR batch per call; per-call latencies (microseconds) into
+ * lat_us[0..n_calls).  Returns n_calls or a negative VMIS_ERR_*. */
+long long vmis_predict_latency_test(const vmis_index_t* index, const uint64_t* q_items, const uint32_t* q_off, uint32_t n_q,
+                                    uint32_t k, uint32_t m, uint32_t how_many, int enable_business_logic, uint32_t n_calls,
+                                    float* lat_us);
 
 /* ---- misc ---------------------------------------------------------------- */
 

@@ -197,4 +197,26 @@ long long vmis_batcher_load_test(vmis_batcher_t* b, const uint64_t* q_items, con
   return (long long)done.load();
 }
 
+// Closed-loop lone caller (bench.py "latency" section): n_calls vmis_predict() calls from THIS thread over the evolving
+// sessions of a CSR batch, one session per call — the reference's own call shape (mod.rs:118-125) without a Python
+// interpreter between the calls.  Per-call latencies (microseconds) go to lat_us[0..n_calls); returns n_calls or a
+// negative VMIS_ERR_*.
+long long vmis_predict_latency_test(const vmis_index_t* index, const uint64_t* q_items, const uint32_t* q_off, uint32_t n_q,
+                                    uint32_t k, uint32_t m, uint32_t how_many, int enable_business_logic, uint32_t n_calls,
+                                    float* lat_us) {
+  if (!index || !q_items || !q_off || n_q == 0 || !lat_us) return VMIS_ERR_ARG;
+  using clock = std::chrono::steady_clock;
+  std::vector<uint64_t> ids(std::max(how_many, 1u)); std::vector<double> sc(ids.size());
+  for (uint32_t j = 0; j < n_calls; ++j) {
+    const uint32_t q = j % n_q;
+    const auto t0 = clock::now();
+    const int rc = vmis_predict(index, q_items + q_off[q], q_off[q + 1] - q_off[q], k, m, how_many, enable_business_logic,
+                                ids.data(), sc.data());
+    const auto t1 = clock::now();
+    if (rc < 0) return rc;
+    lat_us[j] = (float)std::chrono::duration<double, std::micro>(t1 - t0).count();
+  }
+  return (long long)n_calls;
+}
+
 }  // extern "C"

@@ -5,6 +5,8 @@
 #include <cuda_runtime.h>
 
 #include <algorithm>
+#include <atomic>
+#include <chrono>
 #include <cstdarg>
 #include <cstdio>
 #include <cstdlib>
@@ -349,24 +351,50 @@ int host_batch(const vmis_index* cix, const uint64_t* q_items, const uint32_t* q
       const size_t ni = q_off[n_q];
       if (ni) std::memcpy(p + o_items, q_items, ni * 8);
       std::memcpy(p + o_off, q_off, (size_t(n_q) + 1) * 4);
-      CU_TRY(cudaStreamWaitEvent(c->stream, c->done, 0));
       // A handful of sessions (the reference's own call shape, mod.rs:118-125): the kernel reads the query from and
-      // writes the result to the mapped pinned buffer directly — no copy commands, one launch and one sync per call.
+      // writes the result to the mapped pinned buffer directly — no copy commands and no stream synchronisation: the
+      // row counts double as completion flags (written last, behind a system-wide fence) and the caller polls them.
       const bool zero_copy = n_q <= 16 && c->pinned_dev != nullptr;
+      const bool flags = zero_copy && !nb_mode;
+      constexpr uint32_t kPending = 0xFFFFFFFEu;                    // never a count (VMIS_COUNT_TOO_LONG is all ones)
+      volatile uint32_t* done_flag = reinterpret_cast<volatile uint32_t*>(p + o_cnt);
+      if (flags) for (uint32_t q = 0; q < n_q; ++q) done_flag[q] = kPending;
       if (zero_copy) b = static_cast<unsigned char*>(c->pinned_dev);
-      else CU_TRY(cudaMemcpyAsync(b, p, o_ids, cudaMemcpyHostToDevice, c->stream));
+      else {
+        CU_TRY(cudaStreamWaitEvent(c->stream, c->done, 0));
+        CU_TRY(cudaMemcpyAsync(b, p, o_ids, cudaMemcpyHostToDevice, c->stream));
+      }
       vmis::PredictArgs a{};
       a.q_items = reinterpret_cast<const uint64_t*>(b + o_items);
       a.q_off = reinterpret_cast<const uint32_t*>(b + o_off);
       a.n_q = n_q; a.k = k; a.m = m; a.how_many = how_many; a.biz = biz;
+      a.host_flags = flags ? 1 : 0;
       a.out_counts = reinterpret_cast<uint32_t*>(b + o_cnt);
       if (nb_mode) { a.out_sess = reinterpret_cast<uint32_t*>(b + o_ids); a.out_sim = reinterpret_cast<double*>(b + o_sc); }
       else { a.out_ids = reinterpret_cast<uint64_t*>(b + o_ids); a.out_scores = reinterpret_cast<double*>(b + o_sc); }
-      int r = run_device(ix, c, a, plan, c->stream);
+      int r = run_device(ix, c, a, plan, c->stream);               // records c->done behind the kernel
       if (r) return r;
-      if (!zero_copy) CU_TRY(cudaMemcpyAsync(p + o_ids, b + o_ids, total - o_ids, cudaMemcpyDeviceToHost, c->stream));
-      CU_TRY(cudaEventRecord(c->done, c->stream));
-      CU_TRY(cudaStreamSynchronize(c->stream));
+      if (!zero_copy) {
+        CU_TRY(cudaMemcpyAsync(p + o_ids, b + o_ids, total - o_ids, cudaMemcpyDeviceToHost, c->stream));
+        CU_TRY(cudaEventRecord(c->done, c->stream));
+      }
+      bool complete = false;
+      if (flags) {
+        // poll the flags for a while (a lone query takes ~10 us on the device); a kernel that takes longer, or one that
+        // failed and will never raise them, is picked up by the stream synchronisation below
+        const auto t_end = std::chrono::steady_clock::now() + std::chrono::microseconds(300);
+        for (uint32_t spin = 0;; ++spin) {
+          uint32_t q = 0;
+          while (q < n_q && done_flag[q] != kPending) ++q;
+          if (q == n_q) { complete = true; break; }
+          if ((spin & 63u) == 63u && std::chrono::steady_clock::now() > t_end) break;
+#if defined(__x86_64__) || defined(__i386__)
+          __builtin_ia32_pause();
+#endif
+        }
+        std::atomic_thread_fence(std::memory_order_acquire);
+      }
+      if (!complete) CU_TRY(cudaStreamSynchronize(c->stream));
       if (nb_mode) {
         if (k) { std::memcpy(out_sess, p + o_ids, size_t(n_q) * k * 4); std::memcpy(out_sim, p + o_sc, size_t(n_q) * k * 8); }
       } else if (how_many) {

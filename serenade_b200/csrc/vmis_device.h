@@ -71,6 +71,7 @@ struct PredictArgs {
   uint32_t n_q;
   uint32_t k, m, how_many;
   int biz;
+  int host_flags;             // predict mode, outputs in mapped host memory: out_counts[q] is written last, after a system-wide fence
   // outputs (device); predict mode
   uint64_t* out_ids;
   double* out_scores;

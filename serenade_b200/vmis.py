@@ -95,6 +95,7 @@ def load_library():
         "vmis_batcher_stats": (i32, [vp, _u64p, _u64p]),
         "vmis_batcher_destroy": (None, [vp]),
         "vmis_batcher_load_test": (C.c_longlong, [vp, _u64p, _u32p, u32, u32, f64, u32, C.POINTER(C.c_float), sz, _f64p]),
+        "vmis_predict_latency_test": (C.c_longlong, [vp, _u64p, _u32p, u32, u32, u32, u32, i32, u32, C.POINTER(C.c_float)]),
         "vmis_server_create": (vp, [vp, u32, u32, u32, u32, i32, u32, u32, u64, u64]),
         "vmis_server_recommend": (i32, [vp, C.c_char_p, u64, i32, _u64p, _f64p]),
         "vmis_server_session_window": (i32, [vp, C.c_char_p, u64, i32, _u64p, sz]),
@@ -124,7 +125,7 @@ EXPORTED_SYMBOLS = ("vmis_index_from_csv", "vmis_index_from_csv_ex", "vmis_sessi
                     "vmis_predict_batch_device", "vmis_predict", "vmis_find_neighbors_batch", "vmis_items_for_session",
                     "vmis_idf", "vmis_find_attributes", "vmis_postings", "vmis_session_timestamp",
                     "vmis_synth_sessions", "vmis_synth_queries", "vmis_batcher_create", "vmis_batcher_predict",
-                    "vmis_batcher_stats", "vmis_batcher_destroy", "vmis_batcher_load_test", "vmis_server_create", "vmis_server_recommend",
+                    "vmis_batcher_stats", "vmis_batcher_destroy", "vmis_batcher_load_test", "vmis_predict_latency_test", "vmis_server_create", "vmis_server_recommend",
                     "vmis_server_session_window", "vmis_server_stored_items", "vmis_server_set_clock", "vmis_server_stats",
                     "vmis_server_destroy", "vmis_md5", "vmis_last_error", "vmis_last_error_code",
                     "vmis_version")
