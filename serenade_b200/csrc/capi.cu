@@ -337,7 +337,11 @@ int host_batch(const vmis_index* cix, const uint64_t* q_items, const uint32_t* q
       r = ensure(&c->buf, &c->buf_cap, total);
       if (r) return r;
     }
-    // latency path: a small batch is staged through pinned memory, one copy in, one launch, one copy out
+    // latency path: a small batch goes through one mapped pinned buffer.  The kernel writes every result row straight
+    // into it (posted writes over PCIe, no copy command) and raises the row's count last, behind a system-wide fence;
+    // the caller polls the counts and copies finished rows to the output buffers WHILE the kernel is still running, so
+    // neither a device-to-host copy nor a stream synchronisation nor the final memcpy is on the critical path.
+    // A handful of sessions (the reference's own call shape, mod.rs:118-125) are also READ from the mapped buffer.
     if (!stream_ && n_chunks == 1 && total <= (size_t(1) << 20)) {
       CallCtx* c = ring[0].get();
       if (c->pinned_cap < total) {
@@ -348,60 +352,70 @@ int host_batch(const vmis_index* cix, const uint64_t* q_items, const uint32_t* q
       }
       unsigned char* b = static_cast<unsigned char*>(c->buf);
       unsigned char* p = static_cast<unsigned char*>(c->pinned);
+      unsigned char* pd = static_cast<unsigned char*>(c->pinned_dev);
       const size_t ni = q_off[n_q];
       if (ni) std::memcpy(p + o_items, q_items, ni * 8);
       std::memcpy(p + o_off, q_off, (size_t(n_q) + 1) * 4);
-      // A handful of sessions (the reference's own call shape, mod.rs:118-125): the kernel reads the query from and
-      // writes the result to the mapped pinned buffer directly — no copy commands and no stream synchronisation: the
-      // row counts double as completion flags (written last, behind a system-wide fence) and the caller polls them.
-      const bool zero_copy = n_q <= 16 && c->pinned_dev != nullptr;
-      const bool flags = zero_copy && !nb_mode;
+      const bool mapped = pd != nullptr;
+      // more sessions: one H2D copy instead of two PCIe reads per CTA (same-box A/B on launches of 1024: 16 / 256 / 4096
+      // sessions as the limit give 9.45 / 9.46 / 8.97 M qps end to end; the lone call is indifferent)
+      const bool in_mapped = mapped && n_q <= 16;
+      const bool flags = mapped && !nb_mode;                        // find_neighbors rows: plain copy back
       constexpr uint32_t kPending = 0xFFFFFFFEu;                    // never a count (VMIS_COUNT_TOO_LONG is all ones)
       volatile uint32_t* done_flag = reinterpret_cast<volatile uint32_t*>(p + o_cnt);
       if (flags) for (uint32_t q = 0; q < n_q; ++q) done_flag[q] = kPending;
-      if (zero_copy) b = static_cast<unsigned char*>(c->pinned_dev);
-      else {
+      if (!in_mapped) {
         CU_TRY(cudaStreamWaitEvent(c->stream, c->done, 0));
         CU_TRY(cudaMemcpyAsync(b, p, o_ids, cudaMemcpyHostToDevice, c->stream));
       }
+      unsigned char* in = in_mapped ? pd : b;
+      unsigned char* out = flags ? pd : b;
       vmis::PredictArgs a{};
-      a.q_items = reinterpret_cast<const uint64_t*>(b + o_items);
-      a.q_off = reinterpret_cast<const uint32_t*>(b + o_off);
+      a.q_items = reinterpret_cast<const uint64_t*>(in + o_items);
+      a.q_off = reinterpret_cast<const uint32_t*>(in + o_off);
       a.n_q = n_q; a.k = k; a.m = m; a.how_many = how_many; a.biz = biz;
       a.host_flags = flags ? 1 : 0;
-      a.out_counts = reinterpret_cast<uint32_t*>(b + o_cnt);
-      if (nb_mode) { a.out_sess = reinterpret_cast<uint32_t*>(b + o_ids); a.out_sim = reinterpret_cast<double*>(b + o_sc); }
-      else { a.out_ids = reinterpret_cast<uint64_t*>(b + o_ids); a.out_scores = reinterpret_cast<double*>(b + o_sc); }
+      a.out_counts = reinterpret_cast<uint32_t*>(out + o_cnt);
+      if (nb_mode) { a.out_sess = reinterpret_cast<uint32_t*>(out + o_ids); a.out_sim = reinterpret_cast<double*>(out + o_sc); }
+      else { a.out_ids = reinterpret_cast<uint64_t*>(out + o_ids); a.out_scores = reinterpret_cast<double*>(out + o_sc); }
       int r = run_device(ix, c, a, plan, c->stream);               // records c->done behind the kernel
       if (r) return r;
-      if (!zero_copy) {
+      if (!flags) {
         CU_TRY(cudaMemcpyAsync(p + o_ids, b + o_ids, total - o_ids, cudaMemcpyDeviceToHost, c->stream));
         CU_TRY(cudaEventRecord(c->done, c->stream));
-      }
-      bool complete = false;
-      if (flags) {
-        // poll the flags for a while (a lone query takes ~10 us on the device); a kernel that takes longer, or one that
-        // failed and will never raise them, is picked up by the stream synchronisation below
-        const auto t_end = std::chrono::steady_clock::now() + std::chrono::microseconds(300);
-        for (uint32_t spin = 0;; ++spin) {
-          uint32_t q = 0;
-          while (q < n_q && done_flag[q] != kPending) ++q;
-          if (q == n_q) { complete = true; break; }
-          if ((spin & 63u) == 63u && std::chrono::steady_clock::now() > t_end) break;
-#if defined(__x86_64__) || defined(__i386__)
-          __builtin_ia32_pause();
-#endif
-        }
-        std::atomic_thread_fence(std::memory_order_acquire);
-      }
-      if (!complete) CU_TRY(cudaStreamSynchronize(c->stream));
-      if (nb_mode) {
+        CU_TRY(cudaStreamSynchronize(c->stream));
         if (k) { std::memcpy(out_sess, p + o_ids, size_t(n_q) * k * 4); std::memcpy(out_sim, p + o_sc, size_t(n_q) * k * 8); }
-      } else if (how_many) {
-        std::memcpy(out_ids, p + o_ids, size_t(n_q) * how_many * 8);
-        std::memcpy(out_scores, p + o_sc, size_t(n_q) * how_many * 8);
+        std::memcpy(out_counts, p + o_cnt, size_t(n_q) * 4);
+        return VMIS_OK;
       }
-      std::memcpy(out_counts, p + o_cnt, size_t(n_q) * 4);
+      // rows [copied, n_q) are still to be handed over
+      uint32_t copied = 0;
+      auto hand_over = [&](uint32_t upto) {
+        std::atomic_thread_fence(std::memory_order_acquire);
+        const size_t w = how_many;
+        if (w) {
+          std::memcpy(out_ids + size_t(copied) * w, p + o_ids + size_t(copied) * w * 8, size_t(upto - copied) * w * 8);
+          std::memcpy(out_scores + size_t(copied) * w, p + o_sc + size_t(copied) * w * 8, size_t(upto - copied) * w * 8);
+        }
+        for (uint32_t q = copied; q < upto; ++q) out_counts[q] = done_flag[q];
+        copied = upto;
+      };
+      // Poll for a while (a lone query takes ~10 us on the device, 1024 of them ~75 us); a kernel that takes longer, or
+      // one that failed and will never raise its flags, is picked up by the stream synchronisation below.
+      const auto t_end = std::chrono::steady_clock::now() + std::chrono::microseconds(500);
+      for (uint32_t spin = 0; copied < n_q; ++spin) {
+        uint32_t q = copied;
+        while (q < n_q && done_flag[q] != kPending) ++q;
+        if (q == n_q || q - copied >= 128u) { hand_over(q); continue; }
+        if ((spin & 63u) == 63u && std::chrono::steady_clock::now() > t_end) break;
+#if defined(__x86_64__) || defined(__i386__)
+        __builtin_ia32_pause();
+#endif
+      }
+      if (copied < n_q) {
+        CU_TRY(cudaStreamSynchronize(c->stream));
+        hand_over(n_q);
+      }
       return VMIS_OK;
     }
     for (uint32_t ch = 0; ch < n_chunks; ++ch) {
