@@ -198,7 +198,9 @@ __device__ __forceinline__ void fence_async_proxy() { asm volatile("fence.proxy.
 #define VMIS_CLK_FIELDS long long clk[16]; uint32_t nclk;
 #define VMIS_CLK_RESET(S) do { (S).nclk = 0; } while (0)
 #define VMIS_CLK(S) do { if (threadIdx.x == 0 && (S).nclk < 16) (S).clk[(S).nclk++] = clock64(); } while (0)
+#define VMIS_CLK_AFTER(S, v) do { asm volatile("" ::"r"(v)); VMIS_CLK(S); } while (0)   // probe once the value has arrived
 #else
+#define VMIS_CLK_AFTER(S, v) do {} while (0)
 #define VMIS_CLK_FIELDS
 #define VMIS_CLK_RESET(S) do {} while (0)
 #define VMIS_CLK(S) do {} while (0)
@@ -390,14 +392,25 @@ __device__ __forceinline__ void accumulate(const IndexView& ix, SmemLayout& S, c
     uint4 it; int32_t w;
     uint32_t base = grab();
     fetch(base + lane, it, w);
+    VMIS_CLK_AFTER(S, it.x);
+#ifdef VMIS_PHASE_CLOCKS
+    bool first_round = true;
+#endif
     while (base < G) {
       const uint32_t nbase = grab();
       uint4 nit; int32_t nw;                            // next round's granule travels while this one is inserted
       fetch(nbase + lane, nit, nw);
       insert_granule(S, it, w, last_idx, tab, cap, nclaim);
+#ifdef VMIS_PHASE_CLOCKS
+      if (first_round) { VMIS_CLK(S); first_round = false; }
+#endif
       if (guard && over_budget()) break;
       it = nit; w = nw; base = nbase;
     }
+#ifdef VMIS_PHASE_CLOCKS
+    if (first_round) VMIS_CLK(S);
+    VMIS_CLK(S);
+#endif
   } else {
     bool stop = false;
     for (uint32_t i = warp; i < nn && !stop; i += kWarps) {
@@ -1135,7 +1148,7 @@ vmis_predict_kernel(const IndexView ix, const PredictArgs a, const LaunchPlan pl
         VMIS_CLK(S);
         for (uint32_t i = 0; i + 1 < S.nclk && i < N; ++i) a.out_ids[(size_t)q * N + i] = (uint64_t)(S.clk[i + 1] - S.clk[i]);
         for (uint32_t i = S.nclk > 0 ? S.nclk - 1 : 0; i < N; ++i) a.out_ids[(size_t)q * N + i] = 0;
-        if (N > 11) a.out_ids[(size_t)q * N + 11] = S.qcount;
+        if (N > 13) a.out_ids[(size_t)q * N + 13] = S.qcount;
 #endif
         a.out_stats[q] = st;
       }

@@ -458,6 +458,51 @@ def test_chunked_host_api_matches_device_api(sb):
     assert np.array_equal(sess[131_000:], s2) and np.array_equal(sim[131_000:], m2) and np.array_equal(ncnt[131_000:], c2)
 
 
+def test_small_batch_flag_path_matches_device_api(sb):
+    """batches small enough for the mapped pinned buffer: rows are handed over through per-row completion flags while
+    the kernel still runs (capi.cu latency path); sizes around the 16-session zero-copy-input limit and the 128-row
+    hand-over step, then lone callers from several threads at once (pooled call contexts)"""
+    import threading
+    torch = pytest.importorskip("torch")
+    gix = sb.VMISIndex.synth(42, 20_000, 60_000, 1502, 34, 2.0)
+    n_all, n = 2600, 21
+    q_items, q_off = sb.synth_queries(47, 20_000, n_all, 4)
+    dev = torch.device("cuda:0")
+    d_items = torch.from_numpy(q_items.view(np.int64)).to(dev)
+    d_off = torch.from_numpy(q_off.view(np.int32)).to(dev)
+    d_ids = torch.zeros((n_all, n), dtype=torch.int64, device=dev)
+    d_sc = torch.zeros((n_all, n), dtype=torch.float64, device=dev)
+    d_cnt = torch.zeros(n_all, dtype=torch.int32, device=dev)
+    lib = sb.load_library()
+    rc = lib.vmis_predict_batch_device(gix.handle, d_items.data_ptr(), d_off.data_ptr(), n_all, 288, 1502, n, 0,
+                                       d_ids.data_ptr(), d_sc.data_ptr(), d_cnt.data_ptr(), None, None)
+    assert rc == 0, lib.vmis_last_error()
+    torch.cuda.synchronize()
+    r_ids, r_sc, r_cnt = d_ids.cpu().numpy().view(np.uint64), d_sc.cpu().numpy(), d_cnt.cpu().numpy().view(np.uint32)
+    for rep in range(3):                                   # pooled contexts and their buffers are reused
+        for n_q in (1, 2, 16, 17, 127, 128, 129, 1024, 2600):
+            lo = (rep * 37) % (n_all - n_q + 1)
+            sub = (q_items[q_off[lo]:q_off[lo + n_q]], q_off[lo:lo + n_q + 1] - q_off[lo])
+            ids, sc, cnt = sb.predict_batch(gix, sub, 288, 1502, n)
+            assert np.array_equal(cnt, r_cnt[lo:lo + n_q]), (n_q, rep)
+            assert np.array_equal(ids, r_ids[lo:lo + n_q]) and np.array_equal(sc, r_sc[lo:lo + n_q]), (n_q, rep)
+    errs = []
+
+    def lone_caller(t):
+        try:
+            for q in range(t, 400, 8):
+                recs = sb.predict(gix, q_items[q_off[q]:q_off[q + 1]], 288, 1502, n, False)
+                c = int(r_cnt[q])
+                assert [r[0] for r in recs] == list(r_ids[q, :c]) and [r[1] for r in recs] == list(r_sc[q, :c]), q
+        except Exception as e:  # noqa: BLE001
+            errs.append(e)
+
+    th = [threading.Thread(target=lone_caller, args=(t,)) for t in range(8)]
+    [t.start() for t in th]
+    [t.join() for t in th]
+    assert not errs, errs
+
+
 def test_cpp_evaluator_tool(toy_dir, tmp_path):
     """tools/evaluator.cpp (the reference's evaluator binary over include/vmis.hpp): KAT + README run"""
     import subprocess

@@ -24,9 +24,10 @@ else:
     gix = sb.VMISIndex.synth(42, 1_760_000, 11_556_000, M, 34, 2.0, 0, 0, 1)
     n_items = 1_760_000
 dev = torch.device("cuda", 0)
-names = ["phase 0", "phase 1+1b", "phase 2a", "2b insert", "3 score+top4", "3 barrier", "3 sort+push", "3 barrier", "3 tail+sync"]
+names = ["phase 0", "phase 1+1b", "phase 2a", "2b first gather", "2b first round", "2b other rounds", "2b barrier", "3 score+top4", "3 barrier", "3 sort+push",
+         "3 barrier", "3 tail+sync"]
 clk = "clk" in os.environ.get("VMIS_LIB", "")
-for B in (1, 8, 148, 740, 1024, 4096, 1 << 17):
+for B in (1, 8, 148, 740, 1024):
     qi, qo = sb.synth_queries(43 + B, n_items, B, 4)
     di = torch.from_numpy(qi.view(np.int64)).to(dev)
     do = torch.from_numpy(qo.view(np.int32)).to(dev)
@@ -55,5 +56,6 @@ for B in (1, 8, 148, 740, 1024, 4096, 1 << 17):
         call(True)
         torch.cuda.synchronize()
         c = ids.cpu().numpy()[:, :len(names)].astype(np.float64)
+        c = c[(c < 1e7).all(1) & (c[:, 4] > 0)]           # rows of queries whose phase 0 ran ahead carry foreign clocks
         line += "  | cycles: " + "  ".join(f"{n} {c[:, j].mean():.0f}" for j, n in enumerate(names)) + f"  | sum {c.sum(1).mean():.0f}"
     print(line, flush=True)

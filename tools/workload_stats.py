@@ -45,7 +45,7 @@ def run(qi, qo, reps=5):
         lib.vmis_predict_batch_device(gix.handle, di.data_ptr(), do.data_ptr(), n, K, M, N, 0, ids.data_ptr(), sc.data_ptr(),
                                       cnt.data_ptr(), st.data_ptr(), sp)
         torch.cuda.synchronize()
-        return ids.cpu().numpy()[:, :12], e0.elapsed_time(e1) / reps
+        return ids.cpu().numpy()[:, :14], e0.elapsed_time(e1) / reps
     return st.cpu().numpy(), e0.elapsed_time(e1) / reps
 
 
@@ -54,8 +54,9 @@ L = np.diff(qo.astype(np.int64))
 print(f"all: {B} queries {ms:.3f} ms  {B / ms / 1e3:.2f} M qps")
 names = ["postings_visited", "n_neighbors", "neighbor_items", "n_out"]
 if os.environ.get("VMIS_CLOCKS"):
-    names = ["cyc phase 0", "cyc phase 1+1b", "cyc phase 2a", "cyc 2b insert", "cyc 3 score+top4", "cyc 3 barrier", "cyc 3 sort+push",
-             "cyc 3 barrier", "cyc 3 tail+sync", "-", "-", "top-n queue entries"]
+    names = ["cyc phase 0", "cyc phase 1+1b", "cyc phase 2a", "cyc 2b first gather", "cyc 2b first round", "cyc 2b other rounds",
+             "cyc 2b barrier", "cyc 3 score+top4", "cyc 3 barrier", "cyc 3 sort+push", "cyc 3 barrier", "cyc 3 tail+sync", "-",
+             "top-n queue entries"]
 for j, nm in enumerate(names):
     v = st[:, j]
     print(f"  {nm:18s} mean {v.mean():9.1f}  p50 {np.percentile(v, 50):8.0f}  p90 {np.percentile(v, 90):8.0f}  p99 {np.percentile(v, 99):8.0f}  max {v.max()}")
