@@ -114,6 +114,22 @@ __device__ __forceinline__ int warp_incl_scan(int v, int lane) {
   }
   return v;
 }
+// Inclusive warp scan of SMALL values (v < 2^kBits) without a shuffle chain: one ballot per bit, popcounts of the lanes at
+// or below — kBits independent votes instead of five dependent shuffles (merge tiles and the re-deal of collided
+// items: +1.0 %, same-box A/B).
+template <int kBits>
+__device__ __forceinline__ int warp_incl_scan_small(int v, int lane, int& warp_total) {
+  const uint32_t le = kFull >> (31 - lane);
+  int inc = 0, tot = 0;
+#pragma unroll
+  for (int b = 0; b < kBits; ++b) {
+    const uint32_t m = __ballot_sync(kFull, (v >> b) & 1);
+    inc += __popc(m & le) << b;
+    tot += __popc(m) << b;
+  }
+  warp_total = tot;
+  return inc;
+}
 // Block-wide exclusive scan with ONE barrier: warp totals go to a double-buffered scratch row and every warp adds up
 // the totals of the warps before it (two 16-byte broadcast reads, no second shuffle scan).  `par` alternates the row;
 // a row is only rewritten two calls later, i.e. after another barrier, so no trailing barrier is needed.  All threads
@@ -125,6 +141,28 @@ __device__ __forceinline__ int block_excl_scan(int v, ScanScratch& sc, uint32_t&
   par ^= 1u;
   const int inc = warp_incl_scan(v, lane);
   if (lane == 31) row[warp] = inc;
+  __syncthreads();
+  int before = 0, all = 0;
+  if (kWarps == 8) {
+    const int4 a = *reinterpret_cast<const int4*>(row), b = *reinterpret_cast<const int4*>(row + 4);
+    const int t[8] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w};
+#pragma unroll
+    for (int w = 0; w < 8; ++w) { all += t[w]; if (w < warp) before += t[w]; }
+  } else {
+    for (int w = 0; w < kWarps; ++w) { const int t = row[w]; all += t; if (w < warp) before += t; }
+  }
+  total = all;
+  return before + inc - v;
+}
+// the same for small values (v < 2^kBits): ballot scan inside the warps
+template <int kBits>
+__device__ __forceinline__ int block_excl_scan_small(int v, ScanScratch& sc, uint32_t& par, int& total) {
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  int* row = sc.row[par & 1u];
+  par ^= 1u;
+  int wt;
+  const int inc = warp_incl_scan_small<kBits>(v, lane, wt);
+  if (lane == 0) row[warp] = wt;
   __syncthreads();
   int before = 0, all = 0;
   if (kWarps == 8) {
@@ -322,8 +360,9 @@ __device__ __forceinline__ void insert_granule(SmemLayout& S, const uint4 it, in
   for (;;) {
     const int cnt = __popc(pend);
     if (!__any_sync(kFull, cnt != 0)) break;
-    const int incl = warp_incl_scan(cnt, (int)lane);
-    const uint32_t total = (uint32_t)__shfl_sync(kFull, incl, 31);
+    int wt;
+    const int incl = warp_incl_scan_small<3>(cnt, (int)lane, wt);      // cnt <= 4
+    const uint32_t total = (uint32_t)wt;
     uint32_t pos = (uint32_t)(incl - cnt);
     while (pend != 0u && pos < 32u) {
       const uint32_t item = (pend & 1u) ? it.x : (pend & 2u) ? it.y : (pend & 4u) ? it.z : it.w;
@@ -897,7 +936,8 @@ vmis_predict_kernel(const IndexView ix, const PredictArgs a, const LaunchPlan pl
               if ((uint32_t)s < steps) { if (takeA) { pak = ak; ++ai; av = acc[ai]; } else { ++bi; bk = lst[bi]; } }
             }
             int total;
-            uint32_t p = out_count + (uint32_t)block_excl_scan(__popc(vmask), S.scan, par, total);
+            static_assert(kVT < 16, "merge tile counts must fit the 4-bit ballot scan");
+            uint32_t p = out_count + (uint32_t)block_excl_scan_small<(kVT < 8 ? 3 : 4)>(__popc(vmask), S.scan, par, total);
 #pragma unroll
             for (int s = 0; s < kVT; ++s) {
               if ((vmask >> s) & 1u) { if (p < M) out[p] = ((uint64_t)rh[s] << 32) | rl[s]; ++p; }
