@@ -1,15 +1,16 @@
 // serenade_b200/csrc/predict_sm100.cu — the VMIS-kNN predict_next kernel for sm_100a.
 //
-// Persistent CTAs (5 per SM, 256 threads, ~44 KB shared memory) pull evolving sessions from a global work
-// counter (the next two indices are always in flight) and run one query each, end to end in shared memory:
+// Persistent CTAs (5 per SM, 256 threads, ~44 KB shared memory) run one query at a time, end to end in shared memory:
+// CTA b starts with query b, every further one comes from a global work counter (the next two indices are always in
+// flight):
 //
 //   phase 0  de-duplicate the evolving session (vmis_index.rs:335-348), translate external item ids through the
 //            HBM item hash.  For sessions of <= 32 items the LAST WARP does this for the NEXT query while the other
 //            warps insert (phase 2b hands its rounds out dynamically, so nobody waits for it)
 //   phase 1  m-sample: the time-descending posting lists of the distinct items (local HBM, or a peer GPU's HBM over
 //            NVLink when the index is item-sharded) are streamed into shared memory by TMA bulk copies
-//            (cp.async.bulk + mbarrier, double buffered) and folded one by one with a block-wide merge-path merge
-//            that de-duplicates, sums the integer similarity numerators, keeps the first-match position and
+//            (cp.async.bulk + mbarrier; list j+1 is requested when the fold of list j ends) and folded one by one with
+//            a block-wide merge-path merge that de-duplicates, sums the integer similarity numerators, keeps the first-match position and
 //            truncates to the m most recent sessions (closed form of the heap procedure of vmis_index.rs:344-391)
 //   phase 1b top-k neighbours by (numerator desc, recency desc): packed / ballot histogram or binary search for the
 //            threshold numerator, one ordered scan for the ties (vmis_index.rs:394-412)
@@ -879,7 +880,7 @@ vmis_predict_kernel(const IndexView ix, const PredictArgs a, const LaunchPlan pl
       } else {
         uint64_t* acc = acc0;
         uint64_t* out = acc1;
-        // TMA: lists 1 and 2 start streaming into the two staging buffers while list 0 is converted
+        // TMA: list 1 (with two staging buffers also list 2) starts streaming in while list 0 is converted
         auto issue = [&](uint32_t j, uint32_t b) {
           const uint2 ref = j < kRefCache ? S.d_ref[j] : ix.post_ref[S.d_idx[j]];
           const uint32_t bytes = ((min(min(ref.y, M), plan.list_cap) + 3u) & ~3u) * 4u;
